@@ -1,0 +1,80 @@
+"""Generate tests/golden/*.npz from the installed Hugging Face implementation (the arithmetic the
+reference calls).  Run in the build container:  python -m oracle.gen_golden
+
+The fixtures are deliberately small: strided samples of each output plus whole-array statistics, so the
+oracle (and through it the CUDA path) is pinned without committing megabytes.
+Inputs are regenerated from seeds (oracle.frontend.synth_*), weights from oracle.encoder.init_weights.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import encoder as E
+from . import frontend as FE
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+FRAME_STRIDE = 37
+POS_STRIDE = 25
+
+CLIPS = {"noise": FE.synth_noise, "tones": FE.synth_tones, "short": FE.synth_short}
+
+
+def stats(a: np.ndarray) -> np.ndarray:
+    a64 = a.astype(np.float64)
+    return np.array([a64.sum(), a64.min(), a64.max(), np.abs(a64).sum(), (a64 * a64).sum()])
+
+
+def hf_encoder(arch: E.Arch, w: dict):
+    from transformers import WhisperConfig
+    from transformers.models.whisper.modeling_whisper import WhisperEncoder
+
+    cfg = WhisperConfig(
+        d_model=arch.d_model, encoder_layers=arch.layers, encoder_attention_heads=arch.heads,
+        encoder_ffn_dim=arch.ffn, num_mel_bins=arch.n_mels, decoder_layers=1,
+        decoder_attention_heads=arch.heads, decoder_ffn_dim=64, max_source_positions=arch.n_ctx,
+    )
+    enc = WhisperEncoder(cfg).eval().float()
+    missing, unexpected = enc.load_state_dict(w, strict=True)
+    assert not missing and not unexpected
+    return enc
+
+
+def main() -> None:
+    from transformers import WhisperFeatureExtractor
+
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    out = {}
+    for n_mels in (80, 128):
+        fe = WhisperFeatureExtractor(feature_size=n_mels)
+        for name, fn in CLIPS.items():
+            pcm = FE.pad_or_trim(fn())
+            ref = fe._np_extract_fbank_features(pcm[None], "cpu")[0]
+            assert ref.shape == (n_mels, 3000) and ref.dtype == np.float32
+            key = f"logmel{n_mels}_{name}"
+            out[key + "_sub"] = ref[:, ::FRAME_STRIDE].copy()
+            out[key + "_head"] = ref[:, :8].copy()
+            out[key + "_tail"] = ref[:, -8:].copy()
+            out[key + "_stats"] = stats(ref)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "frontend_hf.npz"), **out)
+
+    out = {}
+    torch.manual_seed(0)
+    for arch_name in ("micro", "tiny"):
+        arch = E.ARCHS[arch_name]
+        w = E.round_weights_bf16(E.init_weights(arch, seed=0, ln_jitter=0.02))
+        feats = torch.from_numpy(FE.log_mel(FE.synth_noise(), arch.n_mels))[None]
+        with torch.no_grad():
+            ref = hf_encoder(arch, w)(feats).last_hidden_state[0].numpy()
+        assert ref.shape == (1500, arch.d_model)
+        out[f"enc_{arch_name}_sub"] = ref[::POS_STRIDE].copy()
+        out[f"enc_{arch_name}_stats"] = stats(ref)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "encoder_hf.npz"), **out)
+    for f in ("frontend_hf.npz", "encoder_hf.npz"):
+        print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)), "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,358 @@
+// Non-causal multi-head attention forward for the Whisper encoder on sm_100a (head_dim 64, no mask, scale folded
+// into q):  out = softmax(q k^T) v  per (chunk, head), reference eager_attention_forward / WhisperAttention.forward
+// (transformers/models/whisper/modeling_whisper.py:215-238,284-357).
+//
+// One persistent CTA per SM walks work items (chunk, head, 256 query rows).  Per item, two 128-row query tiles
+// ping-pong over the K/V tiles so the tensor pipe and the exp pipe overlap:
+//   warp 0      TMA producer : Q tiles once per item; K/V 128 x 64 tiles through a 4-stage ring (128B swizzle)
+//   warp 1      MMA issuer   : S_t = Q_t K^T (tcgen05.mma SS, 128x128x64, fp32 in TMEM);
+//                              O_t += P_t V (tcgen05.mma TS: P read from TMEM, V as an MN-major smem operand)
+//   warp 2      TMEM allocator (512 columns: S0 S1 | P0 P1 (bf16 pairs) | O0 O1)
+//   warps 4-7 / 8-11  softmax of tile 0 / 1, one thread per query row: online max with lazy rescale of O
+//                              (only when the running max grows by > 2^8), exp2 on pre-scaled logits, fp32 row sums,
+//                              P written back to TMEM as packed bf16; final O / l -> bf16 -> smem -> TMA store.
+// The 1500 x 1500 score matrix never leaves the SM; keys beyond n_ctx in the last tile are masked to -inf.
+#include "attention_sm100.h"
+#include "gemm_sm100.h"  // encode_tmap
+#include "ptx_sm100.cuh"
+
+namespace ttasr {
+namespace {
+
+constexpr int kTile = 128;          // query rows per tile, keys per KV tile
+constexpr int kHeadDim = 64;
+constexpr int kTileBytes = kTile * kHeadDim * 2;  // 16 KB
+constexpr int kKvStages = 4;
+constexpr int kAttnThreads = 384;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kRescaleThreshold = 8.0f;  // log2 units
+
+// TMEM column map
+constexpr uint32_t kColS = 0;     // S0 at 0, S1 at 128
+constexpr uint32_t kColP = 256;   // P0 at 256, P1 at 320 (128 keys as bf16 pairs = 64 columns)
+constexpr uint32_t kColO = 384;   // O0 at 384, O1 at 448
+
+struct AttnParams {
+  CUtensorMap tm_qkv;  // 3-D (3*d, n_ctx, batch), box (64, 128, 1)
+  CUtensorMap tm_out;  // 3-D (d, n_ctx, batch), box (64, 128, 1)
+  int n_ctx;
+  int n_heads;
+  int d_model;
+  int q_blocks;   // ceil(n_ctx / 256)
+  int kv_tiles;   // ceil(n_ctx / 128)
+  int num_items;  // batch * heads * q_blocks
+};
+
+struct AttnSmem {
+  uint8_t q[2][kTileBytes];
+  uint8_t k[kKvStages][kTileBytes];
+  uint8_t v[kKvStages][kTileBytes];
+  uint8_t o[2][kTileBytes];
+  unsigned long long q_full, q_free;
+  unsigned long long kv_full[kKvStages], kv_free[kKvStages];
+  unsigned long long s_full[2], p_ready[2], o_done[2];
+  uint32_t tmem_ptr;
+};
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t pad = ((smem0 + 1023u) & ~1023u) - smem0;
+  AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw + pad);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tm_qkv);
+    prefetch_tmap(&p.tm_out);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(smem_u32(&s.q_full), 1);
+    mbar_init(smem_u32(&s.q_free), 1);
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(smem_u32(&s.kv_full[i]), 1);
+      mbar_init(smem_u32(&s.kv_free[i]), 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(smem_u32(&s.s_full[t]), 1);
+      mbar_init(smem_u32(&s.p_ready[t]), 4);
+      mbar_init(smem_u32(&s.o_done[t]), 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(smem_u32(&s.tmem_ptr), 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&s.tmem_ptr);
+
+  auto item_coords = [&](int item, int& b, int& h, int& q0) {
+    const int qb = item % p.q_blocks;
+    const int bh = item / p.q_blocks;
+    h = bh % p.n_heads;
+    b = bh / p.n_heads;
+    q0 = qb * 2 * kTile;
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, qphase = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int b, h, q0;
+        item_coords(item, b, h, q0);
+        mbar_wait(smem_u32(&s.q_free), qphase ^ 1);
+        qphase ^= 1;
+        mbar_arrive_expect_tx(smem_u32(&s.q_full), 2 * kTileBytes);
+        tma_load_3d(smem_u32(&s.q[0][0]), &p.tm_qkv, smem_u32(&s.q_full), h * kHeadDim, q0, b);
+        tma_load_3d(smem_u32(&s.q[1][0]), &p.tm_qkv, smem_u32(&s.q_full), h * kHeadDim, q0 + kTile, b);
+        for (int j = 0; j < p.kv_tiles; ++j) {
+          mbar_wait(smem_u32(&s.kv_free[stage]), phase ^ 1);
+          const uint32_t bar = smem_u32(&s.kv_full[stage]);
+          mbar_arrive_expect_tx(bar, 2 * kTileBytes);
+          tma_load_3d(smem_u32(&s.k[stage][0]), &p.tm_qkv, bar, p.d_model + h * kHeadDim, j * kTile, b);
+          tma_load_3d(smem_u32(&s.v[stage][0]), &p.tm_qkv, bar, 2 * p.d_model + h * kHeadDim, j * kTile, b);
+          if (++stage == kKvStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, 0, 0);      // Q (K-major) x K (K-major)
+      constexpr uint32_t idesc_o = umma_idesc_bf16(kTile, kHeadDim, 0, 1);   // P (tmem)   x V (MN-major)
+      int stage = 0;            // stage of KV tile j+1 (S look-ahead)
+      uint32_t phase = 0;
+      uint32_t qphase = 0;
+      uint32_t pphase[2] = {0, 0};
+      auto issue_s = [&](int t, int st) {
+        const uint64_t adesc = umma_desc_sw128(smem_u32(&s.q[t][0]), 16, 1024);
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.k[st][0]), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kHeadDim / 16; ++k)
+          umma_ss<1>(tmem_base + kColS + t * kTile, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(smem_u32(&s.s_full[t]));
+      };
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        mbar_wait(smem_u32(&s.q_full), qphase);
+        qphase ^= 1;
+        mbar_wait(smem_u32(&s.kv_full[stage]), phase);
+        tc_fence_after();
+        issue_s(0, stage);
+        issue_s(1, stage);
+        if (p.kv_tiles == 1) umma_commit(smem_u32(&s.q_free));
+        int cur = stage;
+        if (++stage == kKvStages) { stage = 0; phase ^= 1; }
+        for (int j = 0; j < p.kv_tiles; ++j) {
+          const bool more = (j + 1 < p.kv_tiles);
+          if (more) {
+            mbar_wait(smem_u32(&s.kv_full[stage]), phase);
+            tc_fence_after();
+          }
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(smem_u32(&s.p_ready[t]), pphase[t]);  // softmax done: S_t free, P_t(j) in TMEM
+            pphase[t] ^= 1;
+            tc_fence_after();
+            if (more) issue_s(t, stage);
+            // O_t (+)= P_t V_j : V tile is [128 keys][64] row-major = MN-major B operand, 16 keys per MMA
+            const uint64_t vdesc = umma_desc_sw128(smem_u32(&s.v[cur][0]), kTileBytes, 1024);
+#pragma unroll
+            for (int k = 0; k < kTile / 16; ++k)
+              umma_ts(tmem_base + kColO + t * kHeadDim, tmem_base + kColP + t * 64 + k * 8, vdesc + 128 * k, idesc_o,
+                      (j | k) != 0 ? 1u : 0u);
+            umma_commit(smem_u32(&s.o_done[t]));
+          }
+          umma_commit(smem_u32(&s.kv_free[cur]));  // every MMA that read stage `cur` has been issued
+          if (more) {
+            if (j + 2 == p.kv_tiles) umma_commit(smem_u32(&s.q_free));  // last S of the item issued
+            cur = stage;
+            if (++stage == kKvStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== softmax + output, one thread per query row
+    const int t = (warp - 4) >> 2;          // query tile 0 / 1
+    const int wq = warp & 3;                // TMEM lane quarter
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_base + kColS + t * kTile;
+    const uint32_t p_addr = tmem_base + lane_base + kColP + t * 64;
+    const uint32_t o_addr = tmem_base + lane_base + kColO + t * kHeadDim;
+    const uint32_t bar_id = 1 + t;
+    const bool leader = (wq == 0 && lane == 0);
+    uint32_t sphase = 0, ophase = 0;
+    const int last_valid = p.n_ctx - (p.kv_tiles - 1) * kTile;  // valid keys in the last KV tile
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int b, h, q0;
+      item_coords(item, b, h, q0);
+      float m_used = -INFINITY;  // max the exponentials are taken against (log2 domain), lags the true max
+      float l = 0.f;
+      for (int j = 0; j < p.kv_tiles; ++j) {
+        mbar_wait(smem_u32(&s.s_full[t]), sphase);
+        sphase ^= 1;
+        tc_fence_after();
+        const int valid = (j == p.kv_tiles - 1) ? last_valid : kTile;
+        // pass 1: row max
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c * 32, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float x = (c * 32 + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
+            mx = fmaxf(mx, x);
+          }
+        }
+        const float m_new = fmaxf(m_used, mx * kLog2e);
+        const bool grow = (m_new - m_used) > kRescaleThreshold;  // true on the first tile (m_used = -inf)
+        const bool any_grow = __any_sync(0xffffffffu, grow);
+        if (j > 0) {  // PV(j-1) must have consumed P and finished accumulating into O
+          mbar_wait(smem_u32(&s.o_done[t]), ophase);
+          ophase ^= 1;
+          tc_fence_after();
+        }
+        if (any_grow) {
+          const float factor = (j > 0) ? ex2(m_used - m_new) : 0.f;
+          m_used = m_new;
+          if (j > 0) {
+            l *= factor;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t v[32];
+              tmem_ld_32x32(o_addr + c * 32, v);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
+              tmem_st_32x32(o_addr + c * 32, v);
+            }
+          }
+        }
+        // pass 2: p = 2^(s*log2e - m_used), row sum, packed bf16 -> TMEM
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(s_addr + c * 32, v);
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x0 = (c * 32 + 2 * i < valid) ? __uint_as_float(v[2 * i]) : -INFINITY;
+            const float x1 = (c * 32 + 2 * i + 1 < valid) ? __uint_as_float(v[2 * i + 1]) : -INFINITY;
+            const float p0 = ex2(fmaf(x0, kLog2e, -m_used));
+            const float p1 = ex2(fmaf(x1, kLog2e, -m_used));
+            l += p0 + p1;
+            pk[i] = pack_bf16x2(p0, p1);
+          }
+          tmem_st_32x16(p_addr + c * 16, pk);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.p_ready[t]));
+      }
+      // ---- epilogue: O / l -> bf16 -> swizzled smem -> TMA store
+      mbar_wait(smem_u32(&s.o_done[t]), ophase);
+      ophase ^= 1;
+      tc_fence_after();
+      if (leader) tma_store_wait_read<0>();  // staging tile of the previous item has been read out
+      bar_sync(bar_id, 128);
+      const float inv = 1.0f / l;
+      const uint32_t o_row = smem_u32(&s.o[t][0]) + row * 128;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(o_addr + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = c * 4 + q;  // 16-byte chunk = 8 channels
+          const uint32_t a0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
+          const uint32_t a1 = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
+          const uint32_t a2 = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
+          const uint32_t a3 = pack_bf16x2(__uint_as_float(v[8 * q + 6]) * inv, __uint_as_float(v[8 * q + 7]) * inv);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o_row + ((chunk ^ (row & 7)) << 4)), "r"(a0),
+                       "r"(a1), "r"(a2), "r"(a3)
+                       : "memory");
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      bar_sync(bar_id, 128);
+      if (leader) {
+        tma_store_3d(&p.tm_out, smem_u32(&s.o[t][0]), h * kHeadDim, q0 + t * kTile, b);
+        tma_store_commit();
+      }
+    }
+    if (leader) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<1>(tmem_base, 512);
+}
+
+}  // namespace
+
+cudaError_t attention_launch(const void* qkv, void* out, int batch, int n_ctx, int n_heads, int num_sms,
+                             cudaStream_t stream, const char** why) {
+  static const char* dummy;
+  if (!why) why = &dummy;
+  *why = nullptr;
+  if (!qkv || !out) { *why = "attention: null operand"; return cudaErrorInvalidValue; }
+  if (batch <= 0 || n_ctx <= 0 || n_heads <= 0) { *why = "attention: empty problem"; return cudaErrorInvalidValue; }
+  const int d = n_heads * kHeadDim;
+  AttnParams p{};
+  p.n_ctx = n_ctx;
+  p.n_heads = n_heads;
+  p.d_model = d;
+  p.q_blocks = (n_ctx + 2 * kTile - 1) / (2 * kTile);
+  p.kv_tiles = (n_ctx + kTile - 1) / kTile;
+  p.num_items = batch * n_heads * p.q_blocks;
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(3 * d), static_cast<uint64_t>(n_ctx), static_cast<uint64_t>(batch)};
+    uint64_t str[2] = {dims[0] * 2, dims[0] * dims[1] * 2};
+    uint32_t box[3] = {kHeadDim, kTile, 1};
+    if (encode_tmap(&p.tm_qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, qkv, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B) !=
+        CUDA_SUCCESS) {
+      *why = "attention: cuTensorMapEncodeTiled(qkv) failed";
+      return cudaErrorInvalidValue;
+    }
+  }
+  {
+    uint64_t dims[3] = {static_cast<uint64_t>(d), static_cast<uint64_t>(n_ctx), static_cast<uint64_t>(batch)};
+    uint64_t str[2] = {dims[0] * 2, dims[0] * dims[1] * 2};
+    uint32_t box[3] = {kHeadDim, kTile, 1};
+    if (encode_tmap(&p.tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, out, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B) !=
+        CUDA_SUCCESS) {
+      *why = "attention: cuTensorMapEncodeTiled(out) failed";
+      return cudaErrorInvalidValue;
+    }
+  }
+  const int smem = static_cast<int>(sizeof(AttnSmem)) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
+  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace ttasr

@@ -1,0 +1,332 @@
+// Fused Whisper log-mel front end for sm_100a.
+//
+//   kernel 1  logmel_frames_kernel : PCM -> framing (centre/reflect) -> Hann -> 400-pt FFT -> |.|^2 -> sparse mel
+//                                    -> max(1e-10, .) -> log10 -> raw log-mel [B, n_mels, T] + per-chunk max
+//   kernel 2  logmel_finalize_kernel: max(x, chunk_max - 8), (x + 4) / 4 in place; optional bf16 time-major copy
+//                                    [B, T, n_mels] for the conv stem's implicit GEMM.
+//
+// Reference semantics: HF WhisperFeatureExtractor._np_extract_fbank_features
+// (transformers/models/whisper/feature_extraction_whisper.py:105-133, audio_utils.py:624-832), the extractor the
+// reference repo calls at train_asr.py:607-616.
+//
+// Data movement: a persistent CTA walks tiles of 32 frames; the 5360-sample PCM span of the NEXT tile is brought
+// into shared memory by one cp.async.bulk (TMA 1-D bulk copy, mbarrier completion) while the current tile is
+// transformed, so every PCM byte is read from HBM once (+4.5 % halo, L2 hits).  Twenty threads own one pair of
+// frames: 400 = 20 x 20, each thread a register-resident twiddle-free 20-point PFA DFT (fft400.cuh), one
+// shared-memory transpose between the passes (strides chosen bank-conflict-free), then Hermitian split, power,
+// a gather over the <= 2-nonzero-per-bin mel filters, log10, and 128-byte coalesced stores along time.
+#include "fft400.cuh"
+#include "frontend_logmel.h"
+#include "ptx_sm100.cuh"
+
+namespace ttasr {
+
+namespace {
+
+constexpr int kGroups = 16;                    // frame pairs per tile
+constexpr int kTileFrames = 2 * kGroups;       // 32
+constexpr int kThreads = kRadix * kGroups;     // 320
+constexpr int kSpan = kHop * (kTileFrames - 1) + kNfft;  // 5360 samples per tile
+constexpr int kTStride = 500;                  // per-group stride of the transpose buffer (== 20 mod 32)
+constexpr int kTRow = 25;                      // k1 stride inside a group (== 1 mod 8, >= 20)
+constexpr float kMelFloor = 1e-10f;
+constexpr float kLog10Floor = -10.0f;
+
+struct __align__(16) FrontSmem {
+  float pcm[kSpan];                // raw samples (float, or int16 packed in the first half)
+  float tr[kGroups * kTStride];    // transpose buffer (re); then Z (re); then power of the even frame
+  float ti[kGroups * kTStride];    // (im);                 Z (im);       power of the odd frame
+  float2 tw[kNfft];                // W400^(n2*k1) at [k1*20 + n2]
+  float win[kNfft];
+  float melw[kMaxMelNnz];
+  int mel_lo[kMaxMels];
+  int mel_cnt[kMaxMels];
+  int mel_off[kMaxMels];
+  unsigned long long bar;
+};
+
+template <typename T>
+__device__ __forceinline__ float load_sample(const float* buf, int i);
+template <>
+__device__ __forceinline__ float load_sample<float>(const float* buf, int i) { return buf[i]; }
+template <>
+__device__ __forceinline__ float load_sample<int16_t>(const float* buf, int i) {
+  return static_cast<float>(reinterpret_cast<const int16_t*>(buf)[i]) * (1.0f / 32768.0f);
+}
+
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  if (v >= 0.f)
+    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else
+    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 2)
+logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int* __restrict__ n_valid, int n_samples,
+                     int n_frames, int n_mels, int batch, FrontTables tables, float* __restrict__ raw,
+                     float* __restrict__ chunk_max) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FrontSmem& s = *reinterpret_cast<FrontSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int grp = tid / kRadix;   // frame pair
+  const int sub = tid % kRadix;   // n2 in pass 1, k1 in pass 2
+  const int tiles_per_chunk = (n_frames + kTileFrames - 1) / kTileFrames;
+  const long long total_tiles = static_cast<long long>(batch) * tiles_per_chunk;
+
+  // ---- one-time tables -> shared memory
+  for (int i = tid; i < kNfft; i += kThreads) {
+    s.tw[i] = tables.twiddle[i];
+    s.win[i] = tables.window[i];
+  }
+  for (int i = tid; i < kMaxMelNnz; i += kThreads) s.melw[i] = tables.mel_w[i];
+  for (int i = tid; i < kMaxMels; i += kThreads) {
+    s.mel_lo[i] = tables.mel_lo[i];
+    s.mel_cnt[i] = tables.mel_cnt[i];
+    s.mel_off[i] = tables.mel_off[i];
+  }
+  const uint32_t bar = smem_u32(&s.bar);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const bool rows_aligned = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((row_stride * sizeof(T)) % 16 == 0);
+
+  // tile classification: 0 = all-zero (skip the transform), 1 = interior (bulk copy), 2 = edge (reflect / zero fill)
+  auto classify = [&](long long tile, int& b, int& tt, int& valid) -> int {
+    b = static_cast<int>(tile / tiles_per_chunk);
+    tt = static_cast<int>(tile % tiles_per_chunk);
+    valid = n_valid ? min(max(n_valid[b], 0), n_samples) : n_samples;
+    const int start = tt * kTileFrames * kHop - kNfft / 2;
+    if (start >= valid && valid < n_samples - kNfft) return 0;
+    if (rows_aligned && start >= 0 && start + kSpan <= valid) return 1;
+    return 2;
+  };
+  // bring a tile's PCM span into the staging buffer (asynchronously when interior); caller guarantees it is free
+  auto stage = [&](long long tile) -> int {
+    int b, tt, valid;
+    const int kind = classify(tile, b, tt, valid);
+    const int start = tt * kTileFrames * kHop - kNfft / 2;
+    const T* row = pcm + static_cast<long long>(b) * row_stride;
+    if (kind == 1) {
+      if (tid == 0) {
+        fence_proxy_async_smem();  // earlier generic-proxy accesses to the buffer vs. the async-proxy write
+        mbar_arrive_expect_tx(bar, kSpan * sizeof(T));
+        bulk_load_1d(smem_u32(&s.pcm[0]), row + start, kSpan * sizeof(T), bar);
+      }
+    } else if (kind == 2) {
+      T* dst = reinterpret_cast<T*>(&s.pcm[0]);
+      for (int i = tid; i < kSpan; i += kThreads) {
+        int idx = start + i;
+        if (idx < 0) idx = -idx;  // reflect (edge sample not repeated)
+        if (idx >= n_samples) idx = 2 * n_samples - 2 - idx;
+        T v = T(0);
+        if (idx >= 0 && idx < valid) v = row[idx];
+        dst[i] = v;
+      }
+    }
+    return kind;
+  };
+
+  uint32_t phase = 0;
+  long long tile = blockIdx.x;
+  int kind_cur = 0;
+  if (tile < total_tiles) kind_cur = stage(tile);
+
+  for (; tile < total_tiles; tile += gridDim.x) {
+    const long long next = tile + gridDim.x;
+    int kind_next = 0;
+    int b, tt, valid;
+    classify(tile, b, tt, valid);
+    const int t0 = tt * kTileFrames;
+    float tmax = -INFINITY;
+
+    if (kind_cur == 0) {
+      // every sample the tile touches is zero padding: mel power 0 -> floor
+      for (int idx = tid; idx < kTileFrames * n_mels; idx += kThreads) {
+        const int f = idx % kTileFrames, m = idx / kTileFrames;
+        if (t0 + f < n_frames) raw[(static_cast<long long>(b) * n_mels + m) * n_frames + t0 + f] = kLog10Floor;
+      }
+      tmax = kLog10Floor;
+      if (next < total_tiles) kind_next = stage(next);  // staging buffer is idle on this path
+    } else {
+      if (kind_cur == 1) {
+        mbar_wait(bar, phase);
+        phase ^= 1;
+      } else {
+        __syncthreads();
+      }
+      // ---------------- pass 1: thread (grp, n2) transforms z[20 n1 + n2], n1 = 0..19
+      {
+        const float* x = &s.pcm[0];
+        const int base = grp * 2 * kHop + sub;
+        float xr[20], xi[20], yr[20], yi[20];
+#pragma unroll
+        for (int n1 = 0; n1 < 20; ++n1) {
+          const float w = s.win[20 * n1 + sub];
+          xr[n1] = w * load_sample<T>(x, base + 20 * n1);
+          xi[n1] = w * load_sample<T>(x, base + kHop + 20 * n1);
+        }
+        dft20(xr, xi, yr, yi);
+        float* tr = &s.tr[grp * kTStride + sub];
+        float* ti = &s.ti[grp * kTStride + sub];
+        tr[0] = yr[0];
+        ti[0] = yi[0];
+#pragma unroll
+        for (int k1 = 1; k1 < 20; ++k1) {
+          const float2 w = s.tw[k1 * 20 + sub];
+          tr[k1 * kTRow] = yr[k1] * w.x - yi[k1] * w.y;
+          ti[k1 * kTRow] = yr[k1] * w.y + yi[k1] * w.x;
+        }
+      }
+      __syncthreads();
+      // the PCM span is consumed: fetch the next tile's span under passes 2..4
+      if (next < total_tiles) kind_next = stage(next);
+      // ---------------- pass 2: thread (grp, k1) transforms over n2 -> Z[k1 + 20 k2]
+      {
+        float xr[20], xi[20], yr[20], yi[20];
+        const float* tr = &s.tr[grp * kTStride + sub * kTRow];
+        const float* ti = &s.ti[grp * kTStride + sub * kTRow];
+#pragma unroll
+        for (int n2 = 0; n2 < 20; ++n2) {
+          xr[n2] = tr[n2];
+          xi[n2] = ti[n2];
+        }
+        dft20(xr, xi, yr, yi);
+        __syncthreads();  // everyone has read its transpose rows; the buffer now becomes Z
+        float* zr = &s.tr[grp * kTStride + sub];
+        float* zi = &s.ti[grp * kTStride + sub];
+#pragma unroll
+        for (int k2 = 0; k2 < 20; ++k2) {
+          zr[20 * k2] = yr[k2];
+          zi[20 * k2] = yi[k2];
+        }
+      }
+      __syncthreads();
+      // ---------------- Hermitian split + power: frame a = 2 grp (kept in tr), frame b = 2 grp + 1 (in ti)
+      {
+        float* zr = &s.tr[grp * kTStride];
+        float* zi = &s.ti[grp * kTStride];
+        float pa[11], pb[11];
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+          const int k = sub + kRadix * i;
+          pa[i] = 0.f;
+          pb[i] = 0.f;
+          if (k < kNfreq) {
+            const int kk = (k == 0) ? 0 : kNfft - k;
+            split_power(zr[k], zi[k], zr[kk], zi[kk], pa[i], pb[i]);
+          }
+        }
+        __syncthreads();  // all Z reads done; overwrite with the power spectra
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+          const int k = sub + kRadix * i;
+          if (k < kNfreq) {
+            zr[k] = pa[i];
+            zi[k] = pb[i];
+          }
+        }
+      }
+      __syncthreads();
+      // ---------------- mel gather + log10 + store (lanes walk time -> 128 B coalesced rows)
+      for (int idx = tid; idx < kTileFrames * n_mels; idx += kThreads) {
+        const int f = idx % kTileFrames, m = idx / kTileFrames;
+        const float* p = ((f & 1) ? s.ti : s.tr) + (f >> 1) * kTStride + s.mel_lo[m];
+        const float* w = &s.melw[s.mel_off[m]];
+        const int cnt = s.mel_cnt[m];
+        float acc = 0.f;
+        for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], p[j], acc);
+        const float v = log10f(fmaxf(acc, kMelFloor));
+        if (t0 + f < n_frames) {
+          raw[(static_cast<long long>(b) * n_mels + m) * n_frames + t0 + f] = v;
+          tmax = fmaxf(tmax, v);
+        }
+      }
+      __syncthreads();  // power spectra consumed before the next tile's pass 1 overwrites the buffer
+    }
+    // ---------------- tile max -> chunk max (one atomic per warp)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+    if ((tid & 31) == 0 && tmax > -INFINITY) atomic_max_float(&chunk_max[b], tmax);
+    kind_cur = kind_next;
+  }
+}
+
+// clamp + affine (+ bf16 time-major copy).  One CTA: 32 frames x all mels of one chunk.
+__global__ void __launch_bounds__(256)
+logmel_finalize_kernel(float* __restrict__ feats, const float* __restrict__ chunk_max, int n_frames, int n_mels,
+                       __nv_bfloat16* __restrict__ tmajor, int tmajor_ld) {
+  __shared__ float tile[kMaxMels][33];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * 32;
+  const float lo = chunk_max[b] - 8.0f;
+  float* base = feats + static_cast<long long>(b) * n_mels * n_frames;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int m = wrp; m < n_mels; m += 8) {
+    const int t = t0 + lane;
+    float v = 0.f;
+    if (t < n_frames) {
+      v = base[static_cast<long long>(m) * n_frames + t];
+      v = (fmaxf(v, lo) + 4.0f) * 0.25f;
+      base[static_cast<long long>(m) * n_frames + t] = v;
+    }
+    tile[m][lane] = v;
+  }
+  if (tmajor == nullptr) return;
+  __syncthreads();
+  // [t][m] bf16, channels contiguous (zero for m >= n_mels up to tmajor_ld)
+  for (int idx = threadIdx.x; idx < 32 * (tmajor_ld / 2); idx += 256) {
+    const int f = idx / (tmajor_ld / 2), mp = (idx % (tmajor_ld / 2)) * 2;
+    const int t = t0 + f;
+    if (t >= n_frames) continue;
+    const float v0 = mp < n_mels ? tile[mp][f] : 0.f;
+    const float v1 = mp + 1 < n_mels ? tile[mp + 1][f] : 0.f;
+    reinterpret_cast<uint32_t*>(tmajor + (static_cast<long long>(b) * n_frames + t) * tmajor_ld)[mp / 2] =
+        pack_bf16x2(v0, v1);
+  }
+}
+
+__global__ void fill_kernel(float* p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+}  // namespace
+
+size_t frontend_smem_bytes() { return sizeof(FrontSmem); }
+
+cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
+                          int n_mels, int batch, const FrontTables& tables, float* feats, float* chunk_max,
+                          __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream) {
+  const int n_frames = n_samples / kHop;
+  const int tiles_per_chunk = (n_frames + kTileFrames - 1) / kTileFrames;
+  const long long total = static_cast<long long>(batch) * tiles_per_chunk;
+  if (total == 0) return cudaSuccess;
+  const size_t smem = sizeof(FrontSmem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(logmel_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(logmel_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  fill_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(chunk_max, batch, -INFINITY);
+  const int grid = static_cast<int>(total < 2LL * num_sms ? total : 2LL * num_sms);
+  if (pcm_is_i16)
+    logmel_frames_kernel<int16_t><<<grid, kThreads, smem, stream>>>(static_cast<const int16_t*>(pcm), row_stride, n_valid,
+                                                                   n_samples, n_frames, n_mels, batch, tables, feats,
+                                                                   chunk_max);
+  else
+    logmel_frames_kernel<float><<<grid, kThreads, smem, stream>>>(static_cast<const float*>(pcm), row_stride, n_valid,
+                                                                 n_samples, n_frames, n_mels, batch, tables, feats,
+                                                                 chunk_max);
+  dim3 g2((n_frames + 31) / 32, batch);
+  logmel_finalize_kernel<<<g2, 256, 0, stream>>>(feats, chunk_max, n_frames, n_mels, tmajor, tmajor_ld);
+  return cudaGetLastError();
+}
+
+}  // namespace ttasr

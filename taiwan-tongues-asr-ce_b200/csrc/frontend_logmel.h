@@ -1,0 +1,30 @@
+// Internal interface of the fused log-mel front end (see frontend_logmel.cu).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace ttasr {
+
+constexpr int kMaxMels = 128;
+constexpr int kMaxMelNnz = 512;  // sum over filters of (last_nonzero_bin - first_nonzero_bin + 1); 394 at 128 mels
+
+// device-resident constant tables owned by the front-end handle
+struct FrontTables {
+  const float2* twiddle;  // [400]  W400^(n2*k1) = (cos, -sin)(2 pi n2 k1 / 400) at [k1*20 + n2]
+  const float* window;    // [400]  periodic Hann
+  const float* mel_w;     // [kMaxMelNnz] filter weights, filter m occupies [mel_off[m], mel_off[m]+mel_cnt[m])
+  const int* mel_lo;      // [kMaxMels] first frequency bin of filter m
+  const int* mel_cnt;     // [kMaxMels]
+  const int* mel_off;     // [kMaxMels]
+};
+
+size_t frontend_smem_bytes();
+
+// feats: [B, n_mels, n_samples/160] fp32 (HF layout).  tmajor (optional): [B, T, tmajor_ld] bf16, zero-padded channels.
+// n_valid (optional, device): samples >= n_valid[b] are treated as zero and never read.
+cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
+                          int n_mels, int batch, const FrontTables& tables, float* feats, float* chunk_max,
+                          __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream);
+
+}  // namespace ttasr

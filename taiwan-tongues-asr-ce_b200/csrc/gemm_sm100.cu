@@ -1,0 +1,468 @@
+// tcgen05 GEMM family for the Whisper encoder on sm_100a:
+//     out[M, N] = act(A[M, K] * W[N, K]^T + bias[N]) (+ addend[M, N])
+// used for QKV / out-proj / fc1 / fc2 (modeling_whisper.py:279-282,355,376-377) and, as an implicit GEMM over three
+// shifted (conv1) or parity-split (conv2, stride 2) TMA views of the time-major input, for the two-layer conv stem
+// (modeling_whisper.py:567-568,619-625).
+//
+// Shape of the kernel (one persistent CTA, or CTA pair with cta_group::2, per SM):
+//   warp 0  TMA producer   : A tile 128 x 64 and W tile (BN / CG) x 64 per k-block, 128B-swizzled, STAGES-deep ring
+//   warp 1  MMA issuer     : one elected thread, tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), M = 128 * CG, N = BN,
+//                            accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
+//                            overlaps the MMAs of tile i+1
+//   warp 2  TMEM allocator
+//   warps 4-7 epilogue     : tcgen05.ld -> bias / GELU / residual (addend tile prefetched by TMA into the same
+//                            swizzled staging slab) -> st.shared -> TMA store (clips the M tail)
+// Tiles are walked n-fastest so the CTAs of a wave share a few A row-blocks and all of W in L2.
+#include "gemm_sm100.h"
+#include "ptx_sm100.cuh"
+
+namespace ttasr {
+
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kBK = 64;
+constexpr int kUmmaK = 16;
+constexpr int kSlabBytes = kBM * 128;  // staging slab: 128 rows x 128 B
+constexpr int kThreadsGemm = 256;
+constexpr int kEpiBarrier = 1;
+constexpr int kMaxSmem = 232448;  // 227 KB
+
+template <int BN, int CG>
+struct Cfg {
+  static constexpr int kABytes = kBM * kBK * 2;
+  static constexpr int kBRows = BN / CG;
+  static constexpr int kBBytes = kBRows * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kNBuf = 4;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kStagesRaw = (kMaxSmem - 1024 - kBarBytes - kNBuf * kSlabBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = 1024 + kStages * kStageBytes + kNBuf * kSlabBytes + kBarBytes;
+  static_assert(kStages >= 3, "pipeline too shallow");
+  static_assert(kTmemCols == 256 || kTmemCols == 512, "TMEM columns must be a power of two");
+};
+
+struct GemmParams {
+  CUtensorMap tm_a;    // 4-D (channel, parity, row, batch)
+  CUtensorMap tm_w;    // 2-D (k, n)
+  CUtensorMap tm_out;  // 3-D (n, row, batch)
+  CUtensorMap tm_add;  // 3-D (n, row, batch|1)
+  const float* bias;
+  int mode;
+  int k_blocks;
+  int kb_per_tap;
+  int tiles_m_per_batch;
+  int tiles_n;
+  int num_tiles;
+  int add_bcast;
+};
+
+__device__ __forceinline__ void lds128(uint32_t addr, float4& v) {
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ float apply_act(float x) {
+  if constexpr (ACT == 1) return gelu_erf(x);
+  return x;
+}
+
+template <int BN, int CG, int ACT, bool HAS_ADD, bool OUT_F32>
+__global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
+  using C = Cfg<BN, CG>;
+  constexpr int kStages = C::kStages;
+  constexpr int kNBuf = C::kNBuf;
+  constexpr int kSlabCols = OUT_F32 ? 32 : 64;
+  constexpr int kNSlab = BN / kSlabCols;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = smem_u32(smem_raw);
+  const uint32_t base = (smem0 + 1023u) & ~1023u;
+  const uint32_t sA = base;
+  const uint32_t sB = sA + kStages * C::kABytes;
+  const uint32_t sE = sB + kStages * C::kBBytes;
+  const uint32_t sBar = sE + kNBuf * kSlabBytes;
+  auto full_bar = [&](int i) { return sBar + 8u * i; };
+  auto empty_bar = [&](int i) { return sBar + 8u * (kStages + i); };
+  auto tfull_bar = [&](int i) { return sBar + 8u * (2 * kStages + i); };
+  auto tempty_bar = [&](int i) { return sBar + 8u * (2 * kStages + 2 + i); };
+  auto add_bar = [&](int i) { return sBar + 8u * (2 * kStages + 4 + i); };
+  const uint32_t tmem_slot = sBar + 8u * (2 * kStages + 4 + kNBuf);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem0));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tm_a);
+    prefetch_tmap(&p.tm_w);
+    prefetch_tmap(&p.tm_out);
+    if (HAS_ADD) prefetch_tmap(&p.tm_add);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(full_bar(i), 1);
+      mbar_init(empty_bar(i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4 * CG);
+    }
+    for (int i = 0; i < kNBuf; ++i) mbar_init(add_bar(i), 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<CG>(tmem_slot, C::kTmemCols);
+    tmem_relinquish<CG>();
+  }
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int tile, int& b, int& t0, int& n0) {
+    const int nt = tile % p.tiles_n;
+    const int mt = tile / p.tiles_n;
+    b = mt / p.tiles_m_per_batch;
+    t0 = (mt % p.tiles_m_per_batch) * (kBM * CG) + static_cast<int>(rank) * kBM;
+    n0 = nt * BN;
+  };
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        int b, t0, n0;
+        tile_coords(tile, b, t0, n0);
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const int tap = kb / p.kb_per_tap;
+          const int c0 = (kb - tap * p.kb_per_tap) * kBK;
+          int parity = 0, row = t0;
+          if (p.mode == kGemmPlain) {
+            // c0 walks K
+          } else if (p.mode == kGemmConv1) {
+            row = t0 + tap - 1;
+          } else {
+            parity = (tap == 1) ? 0 : 1;
+            row = t0 + (tap == 0 ? -1 : 0);
+          }
+          const uint32_t dst_a = sA + stage * C::kABytes;
+          const uint32_t dst_b = sB + stage * C::kBBytes;
+          if constexpr (CG == 1) {
+            const uint32_t bar = full_bar(stage);
+            mbar_arrive_expect_tx(bar, C::kStageBytes);
+            tma_load_4d(dst_a, &p.tm_a, bar, c0, parity, row, b);
+            tma_load_2d(dst_b, &p.tm_w, bar, kb * kBK, n0);
+          } else {
+            if (rank == 0) mbar_arrive_expect_tx(full_bar(stage), 2 * C::kStageBytes);
+            const uint32_t bar = mapa(full_bar(stage), 0);  // the leader CTA's barrier collects both CTAs' bytes
+            tma_load_4d_cg2(dst_a, &p.tm_a, bar, c0, parity, row, b);
+            tma_load_2d_cg2(dst_b, &p.tm_w, bar, kb * kBK, n0 + static_cast<int>(rank) * C::kBRows);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer (leader CTA of the pair)
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBM * CG, BN, 0, 0);
+      int stage = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        mbar_wait_cluster(tempty_bar(as), aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BN;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(sA + stage * C::kABytes, 16, 1024);
+          const uint64_t bdesc = umma_desc_sw128(sB + stage * C::kBBytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBK / kUmmaK; ++k)
+            umma_ss<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (CG == 1) umma_commit(empty_bar(stage)); else umma_commit_cg2(empty_bar(stage), 0x3);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if constexpr (CG == 1) umma_commit(tfull_bar(as)); else umma_commit_cg2(tfull_bar(as), 0x3);
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== epilogue
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    const bool e0 = (threadIdx.x == 128);
+    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+    const uint32_t row_off = row * 128;
+    const uint32_t swz = row & 7;
+    int as = 0;
+    uint32_t aphase = 0;
+    uint32_t g = 0;  // running slab counter -> staging buffer g % kNBuf
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      int b, t0, n0;
+      tile_coords(tile, b, t0, n0);
+      const int add_b = p.add_bcast ? 0 : b;
+      if (HAS_ADD && e0) {
+        tma_store_wait_read<kNBuf - 1>();
+        const uint32_t bar = add_bar(g % kNBuf);
+        mbar_arrive_expect_tx(bar, kSlabBytes);
+        tma_load_3d(sE + (g % kNBuf) * kSlabBytes, &p.tm_add, bar, n0, t0, add_b);
+      }
+      mbar_wait(tfull_bar(as), aphase);
+      tc_fence_after();
+      const uint32_t acc_addr = tmem_base + lane_base + as * BN;
+#pragma unroll 1
+      for (int s = 0; s < kNSlab; ++s, ++g) {
+        const uint32_t buf = g % kNBuf;
+        const uint32_t slab = sE + buf * kSlabBytes;
+        if (e0) {
+          if (HAS_ADD) {
+            if (s + 1 < kNSlab) {
+              tma_store_wait_read<kNBuf - 2>();
+              const uint32_t nb = (g + 1) % kNBuf;
+              mbar_arrive_expect_tx(add_bar(nb), kSlabBytes);
+              tma_load_3d(sE + nb * kSlabBytes, &p.tm_add, add_bar(nb), n0 + (s + 1) * kSlabCols, t0, add_b);
+            }
+          } else {
+            tma_store_wait_read<kNBuf - 1>();
+          }
+        }
+        if (!HAS_ADD) bar_sync(kEpiBarrier, 128);  // slab `buf` is free again
+
+        if constexpr (OUT_F32) {
+          uint32_t acc[32];
+          tmem_ld_32x32(acc_addr + s * 32, acc);
+          tmem_wait_ld();
+          if (s == kNSlab - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
+          }
+          if (HAS_ADD) mbar_wait(add_bar(buf), (g / kNBuf) & 1);
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 32);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 bv = __ldg(bias4 + c);
+            const uint32_t addr = slab + row_off + ((c ^ swz) << 4);
+            float4 v;
+            v.x = apply_act<ACT>(__uint_as_float(acc[4 * c + 0]) + bv.x);
+            v.y = apply_act<ACT>(__uint_as_float(acc[4 * c + 1]) + bv.y);
+            v.z = apply_act<ACT>(__uint_as_float(acc[4 * c + 2]) + bv.z);
+            v.w = apply_act<ACT>(__uint_as_float(acc[4 * c + 3]) + bv.w);
+            if (HAS_ADD) {
+              float4 a;
+              lds128(addr, a);
+              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            }
+            sts128(addr, v);
+          }
+        } else {
+          static_assert(OUT_F32 || !HAS_ADD, "bf16 output with an addend is not instantiated");
+          uint32_t acc0[32], acc1[32];
+          tmem_ld_32x32(acc_addr + s * 64, acc0);
+          tmem_ld_32x32(acc_addr + s * 64 + 32, acc1);
+          tmem_wait_ld();
+          if (s == kNSlab - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
+          }
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 64);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {  // 16-byte chunk = 8 bf16 columns
+            const uint32_t* a = (c < 4) ? &acc0[8 * c] : &acc1[8 * (c - 4)];
+            const float4 b0 = __ldg(bias4 + 2 * c), b1 = __ldg(bias4 + 2 * c + 1);
+            const float v0 = apply_act<ACT>(__uint_as_float(a[0]) + b0.x);
+            const float v1 = apply_act<ACT>(__uint_as_float(a[1]) + b0.y);
+            const float v2 = apply_act<ACT>(__uint_as_float(a[2]) + b0.z);
+            const float v3 = apply_act<ACT>(__uint_as_float(a[3]) + b0.w);
+            const float v4 = apply_act<ACT>(__uint_as_float(a[4]) + b1.x);
+            const float v5 = apply_act<ACT>(__uint_as_float(a[5]) + b1.y);
+            const float v6 = apply_act<ACT>(__uint_as_float(a[6]) + b1.z);
+            const float v7 = apply_act<ACT>(__uint_as_float(a[7]) + b1.w);
+            sts128u(slab + row_off + ((c ^ swz) << 4), pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5),
+                    pack_bf16x2(v6, v7));
+          }
+        }
+        fence_proxy_async_smem();
+        bar_sync(kEpiBarrier, 128);
+        if (e0) {
+          tma_store_3d(&p.tm_out, slab, n0 + s * kSlabCols, t0, b);
+          tma_store_commit();
+        }
+      }
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (e0) tma_store_wait<0>();
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  if constexpr (CG == 2) cluster_sync(); else __syncthreads();
+  if (warp == 2) tmem_dealloc<CG>(tmem_base, C::kTmemCols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+template <int BN, int CG, int ACT, bool HAS_ADD, bool OUT_F32>
+cudaError_t launch_variant(const GemmParams& p, int num_sms, cudaStream_t stream) {
+  using C = Cfg<BN, CG>;
+  auto kern = gemm_kernel<BN, CG, ACT, HAS_ADD, OUT_F32>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int clusters = num_sms / CG;
+  if (clusters > p.num_tiles) clusters = p.num_tiles;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kThreadsGemm);
+  cfg.dynamicSmemBytes = C::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+template <int BN, int CG>
+cudaError_t dispatch_epilogue(const GemmCall& c, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  if (c.out_f32) {
+    if (c.addend) {
+      return c.act ? launch_variant<BN, CG, 1, true, true>(p, num_sms, stream)
+                   : launch_variant<BN, CG, 0, true, true>(p, num_sms, stream);
+    }
+    return c.act ? launch_variant<BN, CG, 1, false, true>(p, num_sms, stream)
+                 : launch_variant<BN, CG, 0, false, true>(p, num_sms, stream);
+  }
+  return c.act ? launch_variant<BN, CG, 1, false, false>(p, num_sms, stream)
+               : launch_variant<BN, CG, 0, false, false>(p, num_sms, stream);
+}
+
+}  // namespace
+
+CUresult encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* ptr, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return CUDA_ERROR_NOT_SUPPORTED;
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  return fn(map, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, const char** why) {
+  static const char* dummy;
+  if (!why) why = &dummy;
+  *why = nullptr;
+  if (!c.a || !c.w || !c.out || !c.bias) { *why = "gemm: null operand"; return cudaErrorInvalidValue; }
+  if (c.n % 128 != 0 || c.n <= 0) { *why = "gemm: N must be a positive multiple of 128"; return cudaErrorInvalidValue; }
+  if (c.k_blocks <= 0 || c.kb_per_tap <= 0 || c.rows <= 0 || c.nbatch <= 0) { *why = "gemm: empty problem"; return cudaErrorInvalidValue; }
+  if ((c.lda * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(c.a) & 15) || (reinterpret_cast<uintptr_t>(c.w) & 15) ||
+      (reinterpret_cast<uintptr_t>(c.out) & 15) || (reinterpret_cast<uintptr_t>(c.bias) & 15)) {
+    *why = "gemm: operands must be 16-byte aligned with 16-byte row pitch";
+    return cudaErrorInvalidValue;
+  }
+  if (c.addend && !c.out_f32) { *why = "gemm: addend requires fp32 output"; return cudaErrorInvalidValue; }
+  const int bn = (c.n % 256 == 0) ? 256 : 128;
+  int cg = c.cta_group == 0 ? 2 : c.cta_group;
+  if (cg != 1 && cg != 2) { *why = "gemm: cta_group must be 0, 1 or 2"; return cudaErrorInvalidValue; }
+
+  GemmParams p{};
+  p.bias = c.bias;
+  p.mode = c.mode;
+  p.k_blocks = c.k_blocks;
+  p.kb_per_tap = c.kb_per_tap;
+  p.tiles_m_per_batch = (c.rows + kBM * cg - 1) / (kBM * cg);
+  p.tiles_n = c.n / bn;
+  p.num_tiles = p.tiles_m_per_batch * c.nbatch * p.tiles_n;
+  p.add_bcast = c.addend_bcast;
+
+  CUresult r;
+  {  // A: (channel, parity, row, batch)
+    uint64_t dims[4], str[3];
+    uint32_t box[4] = {static_cast<uint32_t>(kBK), 1, static_cast<uint32_t>(kBM), 1};
+    const uint64_t pitch = static_cast<uint64_t>(c.lda) * 2;
+    if (c.mode == kGemmConv2) {
+      dims[0] = c.a_inner; dims[1] = 2; dims[2] = c.rows; dims[3] = c.nbatch;
+      str[0] = pitch; str[1] = 2 * pitch; str[2] = 2ull * c.rows * pitch;
+    } else {
+      dims[0] = c.a_inner; dims[1] = 1; dims[2] = c.rows; dims[3] = c.nbatch;
+      str[0] = pitch; str[1] = pitch; str[2] = static_cast<uint64_t>(c.rows) * pitch;
+    }
+    r = encode_tmap(&p.tm_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, c.a, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { *why = "gemm: cuTensorMapEncodeTiled(A) failed"; return cudaErrorInvalidValue; }
+  }
+  {  // W: (k, n)
+    uint64_t dims[2] = {static_cast<uint64_t>(c.k_blocks) * kBK, static_cast<uint64_t>(c.n)};
+    uint64_t str[1] = {dims[0] * 2};
+    uint32_t box[2] = {static_cast<uint32_t>(kBK), static_cast<uint32_t>(bn / cg)};
+    r = encode_tmap(&p.tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c.w, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { *why = "gemm: cuTensorMapEncodeTiled(W) failed"; return cudaErrorInvalidValue; }
+  }
+  {  // out: (n, row, batch)
+    const uint64_t esz = c.out_f32 ? 4 : 2;
+    uint64_t dims[3] = {static_cast<uint64_t>(c.n), static_cast<uint64_t>(c.rows), static_cast<uint64_t>(c.nbatch)};
+    uint64_t str[2] = {dims[0] * esz, dims[0] * dims[1] * esz};
+    uint32_t box[3] = {c.out_f32 ? 32u : 64u, static_cast<uint32_t>(kBM), 1};
+    r = encode_tmap(&p.tm_out, c.out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.out,
+                    dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { *why = "gemm: cuTensorMapEncodeTiled(out) failed"; return cudaErrorInvalidValue; }
+  }
+  if (c.addend) {
+    uint64_t dims[3] = {static_cast<uint64_t>(c.n), static_cast<uint64_t>(c.rows),
+                        static_cast<uint64_t>(c.addend_bcast ? 1 : c.nbatch)};
+    uint64_t str[2] = {dims[0] * 4, dims[0] * dims[1] * 4};
+    uint32_t box[3] = {32u, static_cast<uint32_t>(kBM), 1};
+    r = encode_tmap(&p.tm_add, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c.addend, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { *why = "gemm: cuTensorMapEncodeTiled(addend) failed"; return cudaErrorInvalidValue; }
+  }
+
+  if (bn == 256) return cg == 2 ? dispatch_epilogue<256, 2>(c, p, num_sms, stream) : dispatch_epilogue<256, 1>(c, p, num_sms, stream);
+  return cg == 2 ? dispatch_epilogue<128, 2>(c, p, num_sms, stream) : dispatch_epilogue<128, 1>(c, p, num_sms, stream);
+}
+
+}  // namespace ttasr

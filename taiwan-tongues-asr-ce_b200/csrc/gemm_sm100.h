@@ -1,0 +1,45 @@
+// Internal interface of the tcgen05 GEMM / implicit-GEMM-conv kernel family (gemm_sm100.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ttasr {
+
+enum GemmMode {
+  kGemmPlain = 0,  // A[M, K] row-major
+  kGemmConv1 = 1,  // Conv1d k=3 s=1 p=1 over a time-major [B, T, C] input
+  kGemmConv2 = 2,  // Conv1d k=3 s=2 p=1 over a time-major [B, 2*T, C] input (T = output rows per chunk)
+};
+
+struct GemmCall {
+  int mode = kGemmPlain;
+  // A operand (bf16). plain: a[M, lda]; conv: time-major activations [B, T_in, lda]
+  const void* a = nullptr;
+  int64_t lda = 0;          // row stride in elements
+  int a_inner = 0;          // valid channels per row (K for plain; C_in for conv) — reads beyond are zero-filled
+  int rows = 0;             // OUTPUT rows per batch item (M for plain)
+  int nbatch = 1;
+  // B operand: packed weights [N, kp] bf16 row-major, kp = k_blocks * 64 (conv: tap-major, channels padded per tap)
+  const void* w = nullptr;
+  int n = 0;
+  int k_blocks = 0;
+  int kb_per_tap = 0;       // k-blocks per filter tap (== k_blocks for plain)
+  // epilogue: out = act(acc + bias) (+ addend)
+  const float* bias = nullptr;      // [n] fp32 (required; pass zeros for "no bias")
+  const float* addend = nullptr;    // fp32 [nbatch*rows, n] or, if addend_bcast, [rows, n] shared by every batch item
+  int addend_bcast = 0;
+  int act = 0;                      // 0 identity, 1 GELU(erf)
+  void* out = nullptr;              // [nbatch*rows, n]
+  int out_f32 = 0;
+  int cta_group = 0;                // 0 = default, 1, 2
+};
+
+// TMA descriptor helper (driver entry point resolved at run time; libcuda is not linked)
+CUresult encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* ptr, const uint64_t* dims,
+                     const uint64_t* strides_bytes /*rank-1*/, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+// Returns cudaSuccess or the launch error; *why (optional) gets a static string on argument errors.
+cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, const char** why);
+
+}  // namespace ttasr

@@ -1,0 +1,533 @@
+// C ABI (include/ttasr_abi.h) over the sm_100a kernels: handle management, weight packing, the encoder's launch
+// sequence.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include "../../include/ttasr_abi.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "attention_sm100.h"
+#include "fft400.cuh"
+#include "frontend_logmel.h"
+#include "gemm_sm100.h"
+#include "layernorm.h"
+#include "ptx_sm100.cuh"
+
+using namespace ttasr;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) return fail(TTASR_E_CUDA, "%s: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+int check_arch(int device, int* num_sms) {
+  int major = 0, sms = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess)
+    return fail(TTASR_E_CUDA, "no usable CUDA device %d: %s", device, cudaGetErrorString(cudaGetLastError()));
+  if (major != 10)
+    return fail(TTASR_E_ARCH, "device %d has compute capability %d.x; this library only runs on sm_100 (B200)", device, major);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (num_sms) *num_sms = sms;
+  return TTASR_OK;
+}
+
+// ------------------------------------------------------------------------------------------- small device helpers
+__global__ void scale_copy_bf16_kernel(__nv_bfloat16* dst, const __nv_bfloat16* src, long long n, float scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2bfloat16(__bfloat162float(src[i]) * scale);
+}
+__global__ void scale_copy_f32_kernel(float* dst, const float* src, long long n, float scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src ? src[i] * scale : 0.f;
+}
+// conv weight [n_out, c_in, 3] -> tap-major [n_out, 3 * c_pad] (zero padded channels)
+__global__ void pack_conv_kernel(__nv_bfloat16* dst, const __nv_bfloat16* src, int n_out, int c_in, int c_pad) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(n_out) * 3 * c_pad;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % c_pad);
+  const int tap = static_cast<int>((i / c_pad) % 3);
+  const int n = static_cast<int>(i / (3LL * c_pad));
+  dst[i] = c < c_in ? src[(static_cast<long long>(n) * c_in + c) * 3 + tap] : __float2bfloat16(0.f);
+}
+// [B, C, T] fp32 -> [B, T, ld] bf16 (channels zero padded to ld)
+__global__ void feats_to_tmajor_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int T, int ld) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 256 threads: 8 rows per pass
+  for (int r = ty; r < 32; r += 8) {
+    const int c = c0 + r, t = t0 + tx;
+    tile[r][tx] = (c < C && t < T) ? in[(static_cast<long long>(b) * C + c) * T + t] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int t = t0 + r, c = c0 + tx;
+    if (t < T && c < ld) out[(static_cast<long long>(b) * T + t) * ld + c] = __float2bfloat16(tile[tx][r]);
+  }
+}
+
+inline unsigned blocks_for(long long n, int bs) { return static_cast<unsigned>((n + bs - 1) / bs); }
+
+}  // namespace
+
+// =================================================================================================== front end
+struct ttasr_frontend {
+  int device = 0;
+  int num_sms = 0;
+  int n_mels = 0;
+  int n_samples = 0;
+  FrontTables tables{};
+  void* table_mem = nullptr;
+  float* chunk_max = nullptr;  // per-chunk running maxima, capacity max_batch
+  int64_t max_batch = 0;
+};
+
+extern "C" {
+
+int ttasr_abi_version(void) { return TTASR_ABI_VERSION; }
+const char* ttasr_last_error(void) { return g_err; }
+
+int ttasr_device_check(int device) { return check_arch(device, nullptr); }
+
+int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const float* mel_filters, const float* window,
+                          ttasr_frontend_t** out) {
+  if (!out || !mel_filters || !window) return fail(TTASR_E_ARG, "frontend_create: null argument");
+  *out = nullptr;
+  if (n_fft != kNfft || hop != kHop) return fail(TTASR_E_ARG, "frontend_create: only n_fft=400, hop=160 are implemented (got %d, %d)", n_fft, hop);
+  if (n_mels <= 0 || n_mels > kMaxMels) return fail(TTASR_E_SHAPE, "frontend_create: n_mels must be in [1, %d] (got %d)", kMaxMels, n_mels);
+  if (n_samples <= 0 || n_samples % hop != 0) return fail(TTASR_E_SHAPE, "frontend_create: n_samples must be a positive multiple of %d", hop);
+  int device = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  int rc = check_arch(device, &sms);
+  if (rc != TTASR_OK) return rc;
+
+  // ---- host tables
+  std::vector<float2> tw(kNfft);
+  for (int k1 = 0; k1 < kRadix; ++k1)
+    for (int n2 = 0; n2 < kRadix; ++n2) {
+      const double ang = -2.0 * M_PI * static_cast<double>(n2 * k1) / kNfft;
+      tw[k1 * kRadix + n2] = make_float2(static_cast<float>(cos(ang)), static_cast<float>(sin(ang)));
+    }
+  std::vector<float> melw(kMaxMelNnz, 0.f);
+  std::vector<int> lo(kMaxMels, 0), cnt(kMaxMels, 0), off(kMaxMels, 0);
+  int used = 0;
+  for (int m = 0; m < n_mels; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < kNfreq; ++k)
+      if (mel_filters[k * n_mels + m] != 0.f) {
+        if (first < 0) first = k;
+        last = k;
+      }
+    if (first < 0) continue;  // all-zero filter: cnt 0 -> power 0 -> floor
+    const int c = last - first + 1;
+    if (used + c > kMaxMelNnz) return fail(TTASR_E_SHAPE, "frontend_create: mel filter bank too dense (> %d band entries)", kMaxMelNnz);
+    lo[m] = first;
+    cnt[m] = c;
+    off[m] = used;
+    for (int j = 0; j < c; ++j) melw[used + j] = mel_filters[(first + j) * n_mels + m];
+    used += c;
+  }
+
+  ttasr_frontend* h = new ttasr_frontend();
+  h->device = device;
+  h->num_sms = sms;
+  h->n_mels = n_mels;
+  h->n_samples = n_samples;
+  const size_t bytes = sizeof(float2) * kNfft + sizeof(float) * kNfft + sizeof(float) * kMaxMelNnz + 3 * sizeof(int) * kMaxMels;
+  cudaError_t e = cudaMalloc(&h->table_mem, bytes);
+  if (e != cudaSuccess) { delete h; return fail(TTASR_E_NOMEM, "frontend_create: cudaMalloc tables: %s", cudaGetErrorString(e)); }
+  char* pdev = static_cast<char*>(h->table_mem);
+  auto put = [&](const void* src, size_t n) -> const void* {
+    void* dst = pdev;
+    cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+    pdev += n;
+    return dst;
+  };
+  h->tables.twiddle = static_cast<const float2*>(put(tw.data(), sizeof(float2) * kNfft));
+  h->tables.window = static_cast<const float*>(put(window, sizeof(float) * kNfft));
+  h->tables.mel_w = static_cast<const float*>(put(melw.data(), sizeof(float) * kMaxMelNnz));
+  h->tables.mel_lo = static_cast<const int*>(put(lo.data(), sizeof(int) * kMaxMels));
+  h->tables.mel_cnt = static_cast<const int*>(put(cnt.data(), sizeof(int) * kMaxMels));
+  h->tables.mel_off = static_cast<const int*>(put(off.data(), sizeof(int) * kMaxMels));
+  h->max_batch = 1 << 16;
+  e = cudaMalloc(&h->chunk_max, sizeof(float) * h->max_batch);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(h->table_mem);
+    delete h;
+    return fail(TTASR_E_CUDA, "frontend_create: %s", cudaGetErrorString(e));
+  }
+  *out = h;
+  return TTASR_OK;
+}
+
+int ttasr_frontend_max_batch(const ttasr_frontend_t* h, int64_t* out) {
+  if (!h || !out) return fail(TTASR_E_ARG, "frontend_max_batch: null argument");
+  *out = h->max_batch;
+  return TTASR_OK;
+}
+
+int ttasr_frontend_run(const ttasr_frontend_t* h, const void* pcm_dev, int pcm_dtype, int64_t batch, int64_t row_stride,
+                       const int32_t* n_valid_dev, float* feats_dev, void* tmajor_dev, int tmajor_ld, void* stream) {
+  if (!h) return fail(TTASR_E_ARG, "frontend_run: null handle");
+  if (batch < 0 || batch > h->max_batch) return fail(TTASR_E_SHAPE, "frontend_run: batch %lld outside [0, %lld]", (long long)batch, (long long)h->max_batch);
+  if (batch == 0) return TTASR_OK;
+  if (!pcm_dev || !feats_dev) return fail(TTASR_E_ARG, "frontend_run: null buffer");
+  if (pcm_dtype != TTASR_PCM_F32 && pcm_dtype != TTASR_PCM_I16) return fail(TTASR_E_ARG, "frontend_run: bad pcm_dtype %d", pcm_dtype);
+  if (!n_valid_dev && row_stride < h->n_samples) return fail(TTASR_E_SHAPE, "frontend_run: row_stride %lld < n_samples %d without n_valid", (long long)row_stride, h->n_samples);
+  if (tmajor_dev && (tmajor_ld < h->n_mels || (tmajor_ld & 1))) return fail(TTASR_E_SHAPE, "frontend_run: tmajor_ld must be even and >= n_mels");
+  cudaError_t e = launch_logmel(pcm_dev, pcm_dtype == TTASR_PCM_I16, row_stride, n_valid_dev, h->n_samples, h->n_mels,
+                                static_cast<int>(batch), h->tables, feats_dev, h->chunk_max,
+                                static_cast<__nv_bfloat16*>(tmajor_dev), tmajor_ld, h->num_sms,
+                                static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(TTASR_E_CUDA, "frontend_run: launch failed: %s", cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+void ttasr_frontend_destroy(ttasr_frontend_t* h) {
+  if (!h) return;
+  cudaFree(h->table_mem);
+  cudaFree(h->chunk_max);
+  delete h;
+}
+
+}  // extern "C"
+
+// =================================================================================================== encoder
+struct LayerDev {
+  const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *b1, *b2;
+  const __nv_bfloat16 *wqkv, *wo, *w1, *w2;
+};
+
+struct ttasr_encoder {
+  int device = 0, num_sms = 0;
+  ttasr_encoder_cfg cfg{};
+  int c1_pad = 128;        // conv1 input channels padded per tap
+  void* arena = nullptr;   // all packed weights
+  const __nv_bfloat16 *conv1_w = nullptr, *conv2_w = nullptr;
+  const float *conv1_b = nullptr, *conv2_b = nullptr, *pos = nullptr, *lnp_g = nullptr, *lnp_b = nullptr;
+  std::vector<LayerDev> layers;
+};
+
+namespace {
+
+struct WsLayout {
+  size_t x, h, qkv, ffn, total;
+};
+WsLayout ws_layout(const ttasr_encoder_cfg& c, int64_t B) {
+  auto up = [](size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); };
+  const size_t rows = static_cast<size_t>(B) * c.n_ctx;
+  WsLayout w;
+  size_t o = 0;
+  w.x = o;   o += up(rows * c.d_model * 4);
+  w.h = o;   o += up(rows * c.d_model * 2);
+  // qkv region also hosts the bf16 time-major features of the stem (2*n_ctx x 128 <= n_ctx x 3d)
+  w.qkv = o; o += up(std::max(rows * 3 * c.d_model * 2, rows * 2 * 128 * 2));
+  // ffn region also hosts conv1's output [B, 2*n_ctx, d] (ffn >= 2d always holds for Whisper; guarded in create)
+  w.ffn = o; o += up(std::max(rows * c.ffn_dim * 2, rows * 2 * c.d_model * 2));
+  w.total = o;
+  return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ttasr_encoder_create(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, ttasr_encoder_t** out) {
+  if (!cfg || !w || !out || !w->layers) return fail(TTASR_E_ARG, "encoder_create: null argument");
+  *out = nullptr;
+  const int d = cfg->d_model, f = cfg->ffn_dim, L = cfg->n_layers;
+  if (d <= 0 || d % 128 != 0 || d > 1280) return fail(TTASR_E_SHAPE, "encoder_create: d_model must be a multiple of 128, <= 1280 (got %d)", d);
+  if (cfg->n_heads <= 0 || d != cfg->n_heads * 64) return fail(TTASR_E_SHAPE, "encoder_create: head_dim must be 64 (d_model %d, heads %d)", d, cfg->n_heads);
+  if (f <= 0 || f % 128 != 0) return fail(TTASR_E_SHAPE, "encoder_create: ffn_dim must be a multiple of 128 (got %d)", f);
+  if (cfg->n_mels <= 0 || cfg->n_mels > 128 || cfg->n_mels % 8 != 0) return fail(TTASR_E_SHAPE, "encoder_create: n_mels must be a multiple of 8, <= 128 (got %d)", cfg->n_mels);
+  if (cfg->n_ctx <= 0 || L <= 0) return fail(TTASR_E_SHAPE, "encoder_create: n_ctx and n_layers must be positive");
+  int device = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  int rc = check_arch(device, &sms);
+  if (rc != TTASR_OK) return rc;
+  if (!w->conv1_w || !w->conv1_b || !w->conv2_w || !w->conv2_b || !w->pos || !w->ln_post_g || !w->ln_post_b)
+    return fail(TTASR_E_ARG, "encoder_create: null stem / final-norm weight");
+  for (int i = 0; i < L; ++i) {
+    const ttasr_layer_weights& l = w->layers[i];
+    if (!l.ln1_g || !l.ln1_b || !l.wq || !l.bq || !l.wk || !l.wv || !l.bv || !l.wo || !l.bo || !l.ln2_g || !l.ln2_b ||
+        !l.w1 || !l.b1 || !l.w2 || !l.b2)
+      return fail(TTASR_E_ARG, "encoder_create: null weight in layer %d", i);
+  }
+
+  ttasr_encoder* h = new ttasr_encoder();
+  h->device = device;
+  h->num_sms = sms;
+  h->cfg = *cfg;
+  const size_t dd = static_cast<size_t>(d) * d;
+  size_t bytes = 0;
+  auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
+  const size_t conv1_bytes = up(static_cast<size_t>(d) * 3 * h->c1_pad * 2), conv2_bytes = up(3 * dd * 2);
+  bytes += conv1_bytes + conv2_bytes + 2 * up(d * 4) + up(static_cast<size_t>(cfg->n_ctx) * d * 4) + 2 * up(d * 4);
+  const size_t per_layer = up(3 * dd * 2) + up(dd * 2) + 2 * up(static_cast<size_t>(d) * f * 2) + 4 * up(d * 4) +
+                           up(3 * d * 4) + up(d * 4) + up(f * 4) + up(d * 4);
+  bytes += per_layer * L;
+  cudaError_t e = cudaMalloc(&h->arena, bytes);
+  if (e != cudaSuccess) { delete h; return fail(TTASR_E_NOMEM, "encoder_create: cudaMalloc(%zu) for packed weights: %s", bytes, cudaGetErrorString(e)); }
+  char* cur = static_cast<char*>(h->arena);
+  auto take = [&](size_t n) { char* p = cur; cur += up(n); return p; };
+  auto copy_bf16 = [&](const void* src, size_t n, float scale) {
+    __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(take(n * 2));
+    scale_copy_bf16_kernel<<<blocks_for(n, 256), 256>>>(dst, static_cast<const __nv_bfloat16*>(src), n, scale);
+    return dst;
+  };
+  auto copy_f32 = [&](const float* src, size_t n, float scale) {
+    float* dst = reinterpret_cast<float*>(take(n * 4));
+    scale_copy_f32_kernel<<<blocks_for(n, 256), 256>>>(dst, src, n, scale);
+    return dst;
+  };
+  {
+    __nv_bfloat16* c1 = reinterpret_cast<__nv_bfloat16*>(take(static_cast<size_t>(d) * 3 * h->c1_pad * 2));
+    pack_conv_kernel<<<blocks_for(static_cast<long long>(d) * 3 * h->c1_pad, 256), 256>>>(
+        c1, static_cast<const __nv_bfloat16*>(w->conv1_w), d, cfg->n_mels, h->c1_pad);
+    h->conv1_w = c1;
+    __nv_bfloat16* c2 = reinterpret_cast<__nv_bfloat16*>(take(3 * dd * 2));
+    pack_conv_kernel<<<blocks_for(3LL * dd, 256), 256>>>(c2, static_cast<const __nv_bfloat16*>(w->conv2_w), d, d, d);
+    h->conv2_w = c2;
+  }
+  h->conv1_b = copy_f32(w->conv1_b, d, 1.f);
+  h->conv2_b = copy_f32(w->conv2_b, d, 1.f);
+  h->pos = copy_f32(w->pos, static_cast<size_t>(cfg->n_ctx) * d, 1.f);
+  h->lnp_g = copy_f32(w->ln_post_g, d, 1.f);
+  h->lnp_b = copy_f32(w->ln_post_b, d, 1.f);
+  h->layers.resize(L);
+  const float qscale = 0.125f;  // head_dim^-0.5 with head_dim = 64: exact in bf16
+  for (int i = 0; i < L; ++i) {
+    const ttasr_layer_weights& l = w->layers[i];
+    LayerDev& o = h->layers[i];
+    o.ln1_g = copy_f32(l.ln1_g, d, 1.f);
+    o.ln1_b = copy_f32(l.ln1_b, d, 1.f);
+    __nv_bfloat16* wqkv = reinterpret_cast<__nv_bfloat16*>(take(3 * dd * 2));
+    scale_copy_bf16_kernel<<<blocks_for(dd, 256), 256>>>(wqkv, static_cast<const __nv_bfloat16*>(l.wq), dd, qscale);
+    scale_copy_bf16_kernel<<<blocks_for(dd, 256), 256>>>(wqkv + dd, static_cast<const __nv_bfloat16*>(l.wk), dd, 1.f);
+    scale_copy_bf16_kernel<<<blocks_for(dd, 256), 256>>>(wqkv + 2 * dd, static_cast<const __nv_bfloat16*>(l.wv), dd, 1.f);
+    o.wqkv = wqkv;
+    float* bqkv = reinterpret_cast<float*>(take(3 * d * 4));
+    scale_copy_f32_kernel<<<blocks_for(d, 256), 256>>>(bqkv, l.bq, d, qscale);
+    scale_copy_f32_kernel<<<blocks_for(d, 256), 256>>>(bqkv + d, nullptr, d, 0.f);  // k_proj has no bias
+    scale_copy_f32_kernel<<<blocks_for(d, 256), 256>>>(bqkv + 2 * d, l.bv, d, 1.f);
+    o.bqkv = bqkv;
+    o.wo = copy_bf16(l.wo, dd, 1.f);
+    o.bo = copy_f32(l.bo, d, 1.f);
+    o.ln2_g = copy_f32(l.ln2_g, d, 1.f);
+    o.ln2_b = copy_f32(l.ln2_b, d, 1.f);
+    o.w1 = copy_bf16(l.w1, static_cast<size_t>(d) * f, 1.f);
+    o.b1 = copy_f32(l.b1, f, 1.f);
+    o.w2 = copy_bf16(l.w2, static_cast<size_t>(d) * f, 1.f);
+    o.b2 = copy_f32(l.b2, d, 1.f);
+  }
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    cudaFree(h->arena);
+    delete h;
+    return fail(TTASR_E_CUDA, "encoder_create: packing weights failed: %s", cudaGetErrorString(e));
+  }
+  if (static_cast<size_t>(cur - static_cast<char*>(h->arena)) > bytes) {
+    cudaFree(h->arena);
+    delete h;
+    return fail(TTASR_E_NOMEM, "encoder_create: internal arena accounting error");
+  }
+  *out = h;
+  return TTASR_OK;
+}
+
+int ttasr_encoder_workspace_bytes(const ttasr_encoder_t* h, int64_t batch, size_t* out) {
+  if (!h || !out) return fail(TTASR_E_ARG, "encoder_workspace_bytes: null argument");
+  if (batch < 0) return fail(TTASR_E_SHAPE, "encoder_workspace_bytes: negative batch");
+  *out = ws_layout(h->cfg, batch).total;
+  return TTASR_OK;
+}
+
+int ttasr_encoder_launch_count(const ttasr_encoder_t* h, int64_t* out) {
+  if (!h || !out) return fail(TTASR_E_ARG, "encoder_launch_count: null argument");
+  *out = 1 + 2 + 7LL * h->cfg.n_layers + 1;
+  return TTASR_OK;
+}
+
+int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int feats_layout, int tmajor_ld, int64_t batch,
+                          void* workspace_dev, size_t workspace_bytes, void* out_dev, int out_dtype, void* stream_v) {
+  if (!h) return fail(TTASR_E_ARG, "encoder_forward: null handle");
+  if (batch < 0) return fail(TTASR_E_SHAPE, "encoder_forward: negative batch");
+  if (batch == 0) return TTASR_OK;
+  if (!feats_dev || !workspace_dev || !out_dev) return fail(TTASR_E_ARG, "encoder_forward: null buffer");
+  if (out_dtype != TTASR_OUT_BF16 && out_dtype != TTASR_OUT_F32) return fail(TTASR_E_ARG, "encoder_forward: bad out_dtype %d", out_dtype);
+  const ttasr_encoder_cfg& c = h->cfg;
+  if (batch * c.n_ctx * 2 > 0x7fffffffLL) return fail(TTASR_E_SHAPE, "encoder_forward: batch %lld too large for one call", (long long)batch);
+  const WsLayout ws = ws_layout(c, batch);
+  if (workspace_bytes < ws.total) return fail(TTASR_E_NOMEM, "encoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.total);
+  if (reinterpret_cast<uintptr_t>(workspace_dev) & 1023) return fail(TTASR_E_ARG, "encoder_forward: workspace must be 1024-byte aligned");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  char* wsb = static_cast<char*>(workspace_dev);
+  float* x = reinterpret_cast<float*>(wsb + ws.x);
+  __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(wsb + ws.h);
+  __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(wsb + ws.qkv);
+  __nv_bfloat16* ffn = reinterpret_cast<__nv_bfloat16*>(wsb + ws.ffn);
+  const int d = c.d_model, f = c.ffn_dim, T = c.n_ctx, Tin = 2 * c.n_ctx;
+  const int B = static_cast<int>(batch);
+  const char* why = nullptr;
+  cudaError_t e;
+#define GEMM_TRY(call, name)                                                                                      \
+  do {                                                                                                            \
+    e = gemm_launch(call, h->num_sms, stream, &why);                                                              \
+    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: %s: %s", name, why ? why : cudaGetErrorString(e)); \
+  } while (0)
+
+  // ---- stem input as bf16 time-major
+  const __nv_bfloat16* ft;
+  int ld;
+  if (feats_layout == TTASR_FEATS_F32_MEL_MAJOR) {
+    ld = c.n_mels;
+    __nv_bfloat16* dst = qkv;  // scratch: dead before the first QKV GEMM
+    dim3 grid((Tin + 31) / 32, (ld + 31) / 32, B);
+    feats_to_tmajor_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(feats_dev), dst, c.n_mels, Tin, ld);
+    ft = dst;
+  } else if (feats_layout == TTASR_FEATS_BF16_TIME_MAJOR) {
+    if (tmajor_ld < c.n_mels || tmajor_ld % 8 != 0) return fail(TTASR_E_SHAPE, "encoder_forward: tmajor_ld must be a multiple of 8 and >= n_mels");
+    ld = tmajor_ld;
+    ft = static_cast<const __nv_bfloat16*>(feats_dev);
+  } else {
+    return fail(TTASR_E_ARG, "encoder_forward: bad feats_layout %d", feats_layout);
+  }
+  __nv_bfloat16* c1 = ffn;  // conv1 output [B, 2T, d], dead before fc1 of layer 0
+  {
+    GemmCall g;
+    g.mode = kGemmConv1;
+    g.a = ft; g.lda = ld; g.a_inner = c.n_mels; g.rows = Tin; g.nbatch = B;
+    g.w = h->conv1_w; g.n = d; g.kb_per_tap = h->c1_pad / 64; g.k_blocks = 3 * g.kb_per_tap;
+    g.bias = h->conv1_b; g.act = 1; g.out = c1; g.out_f32 = 0;
+    GEMM_TRY(g, "conv1");
+  }
+  {
+    GemmCall g;
+    g.mode = kGemmConv2;
+    g.a = c1; g.lda = d; g.a_inner = d; g.rows = T; g.nbatch = B;
+    g.w = h->conv2_w; g.n = d; g.kb_per_tap = d / 64; g.k_blocks = 3 * g.kb_per_tap;
+    g.bias = h->conv2_b; g.act = 1; g.addend = h->pos; g.addend_bcast = 1; g.out = x; g.out_f32 = 1;
+    GEMM_TRY(g, "conv2");
+  }
+  const long long M = static_cast<long long>(B) * T;
+  for (int i = 0; i < c.n_layers; ++i) {
+    const LayerDev& l = h->layers[i];
+    e = layernorm_launch(x, l.ln1_g, l.ln1_b, hbuf, M, d, 0, stream);
+    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d ln1: %s", i, cudaGetErrorString(e));
+    {
+      GemmCall g;
+      g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
+      g.w = l.wqkv; g.n = 3 * d; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
+      g.bias = l.bqkv; g.out = qkv;
+      GEMM_TRY(g, "qkv");
+    }
+    e = attention_launch(qkv, hbuf, B, T, c.n_heads, h->num_sms, stream, &why);
+    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d attention: %s", i, why ? why : cudaGetErrorString(e));
+    {
+      GemmCall g;
+      g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
+      g.w = l.wo; g.n = d; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
+      g.bias = l.bo; g.addend = x; g.out = x; g.out_f32 = 1;
+      GEMM_TRY(g, "out_proj");
+    }
+    e = layernorm_launch(x, l.ln2_g, l.ln2_b, hbuf, M, d, 0, stream);
+    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d ln2: %s", i, cudaGetErrorString(e));
+    {
+      GemmCall g;
+      g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
+      g.w = l.w1; g.n = f; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
+      g.bias = l.b1; g.act = 1; g.out = ffn;
+      GEMM_TRY(g, "fc1");
+    }
+    {
+      GemmCall g;
+      g.a = ffn; g.lda = f; g.a_inner = f; g.rows = static_cast<int>(M); g.nbatch = 1;
+      g.w = l.w2; g.n = d; g.k_blocks = f / 64; g.kb_per_tap = g.k_blocks;
+      g.bias = l.b2; g.addend = x; g.out = x; g.out_f32 = 1;
+      GEMM_TRY(g, "fc2");
+    }
+  }
+  e = layernorm_launch(x, h->lnp_g, h->lnp_b, out_dev, M, d, out_dtype == TTASR_OUT_F32, stream);
+  if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: final layer norm: %s", cudaGetErrorString(e));
+#undef GEMM_TRY
+  return TTASR_OK;
+}
+
+void ttasr_encoder_destroy(ttasr_encoder_t* h) {
+  if (!h) return;
+  cudaFree(h->arena);
+  delete h;
+}
+
+// =================================================================================================== single ops
+int ttasr_op_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* addend_dev, void* out_dev,
+                  int64_t M, int64_t N, int64_t K, int act, int out_dtype, int cta_group, void* stream) {
+  if (!a_dev || !w_dev || !out_dev) return fail(TTASR_E_ARG, "op_gemm: null buffer");
+  if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0 || N % 128 != 0 || M > 0x7fffffff)
+    return fail(TTASR_E_SHAPE, "op_gemm: need M > 0, N %% 128 == 0, K %% 64 == 0 (got %lld, %lld, %lld)", (long long)M, (long long)N, (long long)K);
+  int device = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  int rc = check_arch(device, &sms);
+  if (rc != TTASR_OK) return rc;
+  static thread_local float* zero_bias = nullptr;
+  static thread_local int64_t zero_n = 0;
+  if (!bias_dev) {
+    if (zero_n < N) {
+      if (zero_bias) cudaFree(zero_bias);
+      CUDA_TRY(cudaMalloc(&zero_bias, sizeof(float) * N));
+      CUDA_TRY(cudaMemset(zero_bias, 0, sizeof(float) * N));
+      zero_n = N;
+    }
+    bias_dev = zero_bias;
+  }
+  GemmCall g;
+  g.a = a_dev; g.lda = K; g.a_inner = static_cast<int>(K); g.rows = static_cast<int>(M); g.nbatch = 1;
+  g.w = w_dev; g.n = static_cast<int>(N); g.k_blocks = static_cast<int>(K / 64); g.kb_per_tap = g.k_blocks;
+  g.bias = bias_dev; g.addend = addend_dev; g.act = act; g.out = out_dev; g.out_f32 = (out_dtype == TTASR_OUT_F32);
+  g.cta_group = cta_group;
+  const char* why = nullptr;
+  cudaError_t e = gemm_launch(g, sms, static_cast<cudaStream_t>(stream), &why);
+  if (e != cudaSuccess) return fail(why ? TTASR_E_ARG : TTASR_E_CUDA, "op_gemm: %s", why ? why : cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+int ttasr_op_layernorm(const float* x_dev, const float* g_dev, const float* b_dev, void* y_dev, int64_t rows, int d,
+                       int out_dtype, void* stream) {
+  if (!x_dev || !g_dev || !b_dev || !y_dev) return fail(TTASR_E_ARG, "op_layernorm: null buffer");
+  if (d <= 0 || d % 128 != 0 || d > 1280) return fail(TTASR_E_SHAPE, "op_layernorm: d must be a multiple of 128, <= 1280");
+  cudaError_t e = layernorm_launch(x_dev, g_dev, b_dev, y_dev, rows, d, out_dtype == TTASR_OUT_F32, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(TTASR_E_CUDA, "op_layernorm: %s", cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+int ttasr_op_attention(const void* qkv_dev, void* out_dev, int64_t batch, int n_ctx, int n_heads, void* stream) {
+  if (!qkv_dev || !out_dev) return fail(TTASR_E_ARG, "op_attention: null buffer");
+  if (batch <= 0 || n_ctx <= 0 || n_heads <= 0) return fail(TTASR_E_SHAPE, "op_attention: empty problem");
+  int device = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  int rc = check_arch(device, &sms);
+  if (rc != TTASR_OK) return rc;
+  const char* why = nullptr;
+  cudaError_t e = attention_launch(qkv_dev, out_dev, static_cast<int>(batch), n_ctx, n_heads, sms, static_cast<cudaStream_t>(stream), &why);
+  if (e != cudaSuccess) return fail(why ? TTASR_E_ARG : TTASR_E_CUDA, "op_attention: %s", why ? why : cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,50 @@
+"""The hot path end to end: 16 kHz PCM chunks -> log-mel -> Whisper encoder hidden states, one object per GPU.
+
+This is what the reference's three inference call sites do per 30 s window inside `WhisperModel.transcribe`
+(asr_core.py:159-167, api/file_asr.py:457-465, api/stt_streaming/src/asr/faster_whisper_asr.py:170-172), batched:
+features never leave the GPU between the two stages (the front end writes the bf16 time-major tensor the conv stem
+reads through TMA).
+"""
+from __future__ import annotations
+
+from . import _lib
+from .encoder import B200WhisperEncoder
+from .feature_extractor import B200WhisperFeatureExtractor
+
+
+class B200LogMelEncoder:
+    def __init__(self, feature_extractor: B200WhisperFeatureExtractor, encoder: B200WhisperEncoder):
+        if feature_extractor.feature_size != encoder.config.num_mel_bins:
+            raise _lib.TtasrError(-2, f"feature_size {feature_extractor.feature_size} != encoder num_mel_bins "
+                                      f"{encoder.config.num_mel_bins}")
+        self.feature_extractor = feature_extractor
+        self.encoder = encoder
+        self.device = encoder.device
+        self._stage = None
+
+    @property
+    def launches_per_call(self) -> int:
+        # fill + frames + finalize (front end) and the encoder's sequence minus its unused fp32->bf16 transpose
+        return 3 + self.encoder.launches_per_forward - 1
+
+    def encode_device(self, pcm, n_valid=None, out_dtype=None):
+        """pcm: CUDA [B, n_samples] float32 / int16 -> [B, 1500, d] CUDA."""
+        _, tm = self.feature_extractor.extract(pcm, n_valid=n_valid, return_time_major=True)
+        return self.encoder.encode(tm, out_dtype=out_dtype, time_major_ld=tm.shape[2])
+
+    def encode_host(self, pcm_host, out_host=None, n_valid=None):
+        """pcm_host: CPU tensor [B, n_samples] (pinned for full-rate copies).  Returns the hidden states on the
+        host when `out_host` (a pinned CPU tensor [B, 1500, d] bf16) is given, else the CUDA tensor."""
+        import torch
+
+        B = pcm_host.shape[0]
+        if self._stage is None or self._stage.shape[0] < B or self._stage.dtype != pcm_host.dtype or \
+                self._stage.shape[1] != pcm_host.shape[1]:
+            self._stage = torch.empty((B, pcm_host.shape[1]), dtype=pcm_host.dtype, device=self.device)
+        dev = self._stage[:B]
+        dev.copy_(pcm_host, non_blocking=True)
+        hidden = self.encode_device(dev, n_valid=n_valid)
+        if out_host is not None:
+            out_host.copy_(hidden, non_blocking=True)
+            return out_host
+        return hidden

@@ -1,0 +1,103 @@
+"""Parity of the fused CUDA log-mel front end (through the C ABI) against the numpy oracle: |diff| <= 1e-4 on the
+final (x + 4) / 4 features, plus the analytic cases of SURVEY.md section 8c."""
+import numpy as np
+import pytest
+
+from oracle import frontend as OF
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _fe(n_mels):
+    from ttasr import B200WhisperFeatureExtractor
+
+    return B200WhisperFeatureExtractor(feature_size=n_mels)
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_logmel_matches_oracle_on_config1_clips(cuda_device, n_mels):
+    import torch
+
+    clips = [OF.pad_or_trim(f()) for f in (OF.synth_noise, OF.synth_tones, OF.synth_short)]
+    clips.append(np.zeros(OF.N_SAMPLES, np.float32))
+    pcm = torch.from_numpy(np.stack(clips)).to(cuda_device)
+    got = _fe(n_mels).extract(pcm).cpu().numpy()
+    assert got.shape == (4, n_mels, 3000) and got.dtype == np.float32
+    for i, c in enumerate(clips):
+        ref = OF.log_mel(c, n_mels)
+        err = np.abs(got[i] - ref).max()
+        assert err <= TOL, f"clip {i}: max abs err {err}"
+    # K1: all-zero PCM -> exactly -1.5 everywhere
+    assert np.all(got[3] == -1.5)
+
+
+def test_golden_fixture(cuda_device):
+    import os
+    import torch
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "frontend_hf.npz"))
+    for n_mels in (80, 128):
+        for name, fn in (("noise", OF.synth_noise), ("tones", OF.synth_tones), ("short", OF.synth_short)):
+            pcm = torch.from_numpy(OF.pad_or_trim(fn())[None]).to(cuda_device)
+            got = _fe(n_mels).extract(pcm)[0].cpu().numpy()
+            key = f"logmel{n_mels}_{name}"
+            assert np.abs(got[:, ::37] - g[key + "_sub"]).max() <= TOL
+            assert np.abs(got[:, :8] - g[key + "_head"]).max() <= TOL
+            assert np.abs(got[:, -8:] - g[key + "_tail"]).max() <= TOL
+            assert abs(got.astype(np.float64).sum() - g[key + "_stats"][0]) <= TOL * got.size
+
+
+def test_int16_input_and_ragged_rows(cuda_device):
+    import torch
+
+    rng = np.random.default_rng(5)
+    lens = [480000, 48000, 16000, 123457, 0]
+    rows16 = [(rng.standard_normal(n) * 3000).astype(np.int16) for n in lens]
+    maxlen = max(lens)
+    host = np.zeros((len(lens), maxlen), np.int16)
+    for i, r in enumerate(rows16):
+        host[i, : len(r)] = r
+    fe = _fe(80)
+    pcm = torch.from_numpy(host).to(cuda_device)
+    nv = torch.tensor(lens, dtype=torch.int32, device=cuda_device)
+    got = fe.extract(pcm, n_valid=nv).cpu().numpy()
+    for i, r in enumerate(rows16):
+        ref = OF.log_mel(r.astype(np.float32) / 32768.0, 80)
+        assert np.abs(got[i] - ref).max() <= TOL, f"row {i} (len {lens[i]})"
+    # K2: frames wholly inside the zero padding sit at the clamp floor == the row minimum
+    assert got[2, :, 2000:].max() == got[2].min()
+    # poison the padding: with n_valid the kernel must not read it
+    host2 = host.copy()
+    for i, n in enumerate(lens):
+        host2[i, n:] = 12345
+    got2 = fe.extract(torch.from_numpy(host2).to(cuda_device), n_valid=nv).cpu().numpy()
+    assert np.array_equal(got, got2)
+
+
+def test_batch_invariance_and_time_major_copy(cuda_device):
+    import torch
+
+    g = torch.Generator(device=cuda_device).manual_seed(1234)
+    pcm = (0.1 * torch.randn((9, OF.N_SAMPLES), generator=g, device=cuda_device)).clamp_(-1, 1)
+    fe = _fe(128)
+    feats, tm = fe.extract(pcm, return_time_major=True)
+    single = fe.extract(pcm[4:5])
+    assert torch.equal(feats[4], single[0])  # K4: bit-identical regardless of batch position
+    assert tm.shape == (9, 3000, 128) and tm.dtype == torch.bfloat16
+    assert torch.equal(tm.transpose(1, 2).float(), feats.to(torch.bfloat16).float())
+    ref = OF.log_mel(pcm[7].cpu().numpy(), 128)
+    assert np.abs(feats[7].cpu().numpy() - ref).max() <= TOL
+
+
+def test_reference_call_surface(cuda_device):
+    """The call train_asr.py:610-616 makes, on the CUDA extractor."""
+    fe = _fe(80)
+    x = OF.synth_short()
+    out = fe(x, sampling_rate=16000, return_attention_mask=True)
+    f = out.get("input_features")[0]
+    assert f.shape == (80, 3000)
+    assert np.abs(f - OF.log_mel(x, 80)).max() <= TOL
+    assert out.get("attention_mask")[0].shape == (3000,) and out["attention_mask"][0].sum() == 300
+    with pytest.raises(ValueError):
+        fe(x, sampling_rate=8000)
