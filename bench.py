@@ -1,0 +1,443 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds/second of the hot path (16 kHz PCM -> log-mel -> Whisper encoder) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload large-v3|small|tiny] [--batch B] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic 30 s chunks per GPU (BASELINE.json configs[2] by
+default: whisper-large-v3, 128-bin, 256 chunks; random-init weights of that architecture, synthetic audio).
+Prints ONE JSON line on rank 0 (see DESIGN.md "Measurement" for every field):
+
+  value        whole-job audio-s/s with the PCM already resident in HBM (CUDA events, max over ranks)
+  e2e          the same metric through the public API with HOST buffers: per step a pinned-host -> device copy of the
+               PCM and a device -> pinned-host read of the hidden states inside the timed region
+  roofline     the dominant kernel's algorithmic FLOP/s (per-launch CUDA events recorded inside the timed steps by
+               the library's stage profiler) against the measured peak in MEASURED_PEAKS.json
+  cpu_baseline the reference's CPU implementation (HF numpy extractor + HF fp32 encoder; oracle port if transformers
+               is missing) timed on this box's host cores on a bounded sample of the same workload
+
+--impl reference times only that CPU implementation, with all host threads, as the driver's reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "taiwan-tongues-asr-ce_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "audio-sec/sec (log-mel+large-v3 encoder)"
+UNIT = "audio-s/s"
+N_SAMPLES = 480000
+CHUNK_SECONDS = 30.0
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+def arch_table(name):
+    from ttasr import EncoderConfig
+
+    return EncoderConfig.named(name)
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference
+def make_cpu_weights(cfg, seed=0):
+    """Random-init encoder weights (std 0.02, LN gain 1 / bias 0) under HF names, on the CPU."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    d, f = cfg.d_model, cfg.encoder_ffn_dim
+    w = {}
+
+    def n(*shape):
+        return torch.randn(*shape, generator=g) * 0.02
+
+    w["conv1.weight"], w["conv1.bias"] = n(d, cfg.num_mel_bins, 3), torch.zeros(d)
+    w["conv2.weight"], w["conv2.bias"] = n(d, d, 3), torch.zeros(d)
+    from oracle.encoder import sinusoids
+
+    w["embed_positions.weight"] = sinusoids(cfg.max_source_positions, d)
+    for i in range(cfg.encoder_layers):
+        p = f"layers.{i}."
+        for ln in ("self_attn_layer_norm", "final_layer_norm"):
+            w[p + ln + ".weight"], w[p + ln + ".bias"] = torch.ones(d), torch.zeros(d)
+        for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            w[p + f"self_attn.{proj}.weight"] = n(d, d)
+            if proj != "k_proj":
+                w[p + f"self_attn.{proj}.bias"] = torch.zeros(d)
+        w[p + "fc1.weight"], w[p + "fc1.bias"] = n(f, d), torch.zeros(f)
+        w[p + "fc2.weight"], w[p + "fc2.bias"] = n(d, f), torch.zeros(d)
+    w["layer_norm.weight"], w["layer_norm.bias"] = torch.ones(d), torch.zeros(d)
+    return w
+
+
+class CpuReference:
+    """The reference's CPU implementation of the path: HF numpy log-mel + HF fp32 WhisperEncoder on all host
+    threads (the reference's CTranslate2 CPU encoder is not installable offline — BASELINE.md section 4); falls back to
+    the oracle port when transformers cannot be imported."""
+
+    def __init__(self, workload: str):
+        import torch
+
+        from oracle import encoder as OE
+
+        self.cfg = arch_table(workload)
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.w = make_cpu_weights(self.cfg)
+        self.arch = OE.Arch(workload, self.cfg.d_model, self.cfg.encoder_layers, self.cfg.encoder_attention_heads,
+                            self.cfg.encoder_ffn_dim, self.cfg.num_mel_bins)
+        self.kind = "port"
+        self.hf_fe = self.hf_enc = None
+        try:
+            from transformers import WhisperFeatureExtractor
+
+            from oracle.gen_golden import hf_encoder
+
+            self.hf_fe = WhisperFeatureExtractor(feature_size=self.cfg.num_mel_bins)
+            self.hf_enc = hf_encoder(self.arch, self.w)
+            self.kind = "reference"
+        except Exception:
+            pass
+
+    def step(self, pcm):
+        """pcm: numpy [n, 480000] fp32 -> hidden states; returns seconds."""
+        import numpy as np
+        import torch
+
+        from oracle import encoder as OE
+        from oracle import frontend as OF
+
+        t0 = time.perf_counter()
+        if self.hf_fe is not None:
+            feats = self.hf_fe._np_extract_fbank_features(pcm, "cpu")
+            with torch.no_grad():
+                out = self.hf_enc(torch.from_numpy(np.ascontiguousarray(feats))).last_hidden_state
+        else:
+            feats = OF.log_mel_batch(pcm, self.cfg.num_mel_bins)
+            out = OE.encoder_forward(torch.from_numpy(feats), self.w, self.arch)
+        assert out.shape[1:] == (self.cfg.max_source_positions, self.cfg.d_model)
+        return time.perf_counter() - t0
+
+
+def synth_pcm_cpu(n, seed=1234):
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    return np.clip(0.1 * rng.standard_normal((n, N_SAMPLES)), -1, 1).astype(np.float32)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    ref = CpuReference(args.workload)
+    per_step = args.ref_chunks
+    pcm = synth_pcm_cpu(per_step)
+    for _ in range(max(1, min(args.warmup, 1))):  # one warm-up pass is enough to page in weights / spin up threads
+        ref.step(pcm)
+    times = [ref.step(pcm) for _ in range(args.steps)]
+    total = sum(times)
+    value = per_step * CHUNK_SECONDS * args.steps / total
+    sample = (f"{per_step} x 30 s chunk(s) per step, {args.steps} steps; HF numpy log-mel + "
+              f"{'HF' if ref.kind == 'reference' else 'oracle-port'} fp32 encoder on CPU (CTranslate2 not installable)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, per_gpu_batch=args.batch),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def workload_config(args, per_gpu_batch):
+    cfg = arch_table(args.workload)
+    return {
+        "workload": f"whisper-{args.workload} ({cfg.num_mel_bins}-bin) log-mel front end + {cfg.encoder_layers}-layer "
+                    f"encoder, {per_gpu_batch} x 30 s synthetic chunks per GPU per step, random-init weights",
+        "chunks_per_gpu_per_step": per_gpu_batch, "chunk_seconds": CHUNK_SECONDS,
+        "parallelism": f"dp{args.gpus} (independent chunks, replicated weights, no collective on the data path)",
+        "l2_policy": "inputs larger than L2 (PCM batch >= 0.49 GB, activations >= 1 GB per kernel)",
+    }
+
+
+def make_gpu_weights(cfg, device, seed=0):
+    import torch
+
+    from ttasr.encoder import EncoderConfig  # noqa: F401
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    d, f = cfg.d_model, cfg.encoder_ffn_dim
+
+    def n(*shape):
+        return (torch.randn(*shape, generator=g, device=device) * 0.02).to(torch.bfloat16)
+
+    def z(k):
+        return torch.zeros(k, device=device)
+
+    def one(k):
+        return torch.ones(k, device=device)
+
+    half = d // 2
+    inc = torch.log(torch.tensor(10000.0)) / (half - 1)
+    inv = torch.exp(-inc * torch.arange(half, device=device))
+    t = torch.arange(cfg.max_source_positions, device=device).view(-1, 1) * inv.view(1, -1)
+    w = {"conv1.weight": n(d, cfg.num_mel_bins, 3), "conv1.bias": z(d), "conv2.weight": n(d, d, 3), "conv2.bias": z(d),
+         "embed_positions.weight": torch.cat([t.sin(), t.cos()], dim=1), "layer_norm.weight": one(d),
+         "layer_norm.bias": z(d)}
+    for i in range(cfg.encoder_layers):
+        p = f"layers.{i}."
+        for ln in ("self_attn_layer_norm", "final_layer_norm"):
+            w[p + ln + ".weight"], w[p + ln + ".bias"] = one(d), z(d)
+        for proj in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            w[p + f"self_attn.{proj}.weight"] = n(d, d)
+            if proj != "k_proj":
+                w[p + f"self_attn.{proj}.bias"] = z(d)
+        w[p + "fc1.weight"], w[p + "fc1.bias"] = n(f, d), z(f)
+        w[p + "fc2.weight"], w[p + "fc2.bias"] = n(d, f), z(d)
+    return w
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.proc = None
+        self.path = os.path.join("/tmp", f"ttasr_clocks_{os.getpid()}.csv")
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(gpu_index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2])); power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import ttasr
+    from ttasr.dp import all_max
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: the product path has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    cfg = arch_table(args.workload)
+    B = args.batch
+    fe = ttasr.B200WhisperFeatureExtractor(feature_size=cfg.num_mel_bins)
+    enc = ttasr.B200WhisperEncoder(cfg, make_gpu_weights(cfg, dev, seed=0))
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    pcm = (0.1 * torch.randn((B, N_SAMPLES), generator=g, device=dev)).clamp_(-1, 1)
+    host_pcm = torch.empty((B, N_SAMPLES), dtype=torch.float32).pin_memory()
+    host_pcm.copy_(pcm)
+    host_out = torch.empty((B, cfg.max_source_positions, cfg.d_model), dtype=torch.bfloat16).pin_memory()
+    stage = torch.empty_like(pcm)
+
+    fe_events = []
+
+    def step_device(record_fe=False):
+        if record_fe:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+        _, tm = fe.extract(pcm, return_time_major=True)
+        if record_fe:
+            b.record()
+            fe_events.append((a, b))
+        return enc.encode(tm, time_major_ld=tm.shape[2])
+
+    def step_host():
+        stage.copy_(host_pcm, non_blocking=True)
+        _, tm = fe.extract(stage, return_time_major=True)
+        hidden = enc.encode(tm, time_major_ld=tm.shape[2])
+        host_out.copy_(hidden, non_blocking=True)
+        return hidden
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, **kw):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn(**kw)
+        e1.record()
+        barrier()
+        return all_max(e0.elapsed_time(e1)), out
+
+    # ---- device-resident arm
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    enc.profile(True)
+    enc.profile_read(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms_total, out = timed(step_device, args.steps, record_fe=True)
+    clocks = sampler.stop() if sampler else None
+    stages = enc.profile_read(reset=True)
+    enc.profile(False)
+    fe_ms = [a.elapsed_time(b) for a, b in fe_events]
+    assert bool(torch.isfinite(out.float()).all()), "non-finite hidden states"
+    value = n_gpus * B * CHUNK_SECONDS * args.steps / (ms_total / 1e3)
+
+    # ---- end-to-end arm (host buffers in, host buffers out)
+    for _ in range(min(args.warmup, 3)):
+        step_host()
+    e2e_ms, _ = timed(step_host, args.steps)
+    e2e_value = n_gpus * B * CHUNK_SECONDS * args.steps / (e2e_ms / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (stage profiler events, per launch)
+    peaks, peak_src = measured_peaks()
+    d, f, T, Hh = cfg.d_model, cfg.encoder_ffn_dim, cfg.max_source_positions, cfg.encoder_attention_heads
+    M = B * T
+    flops_per_launch = {
+        "conv1_gemm": 2.0 * B * 2 * T * 3 * cfg.num_mel_bins * d, "conv2_gemm": 2.0 * M * 3 * d * d,
+        "qkv_gemm": 2.0 * M * d * 3 * d, "attention": 4.0 * B * Hh * T * T * 64, "out_proj_gemm": 2.0 * M * d * d,
+        "fc1_gemm": 2.0 * M * d * f, "fc2_gemm": 2.0 * M * d * f,
+    }
+    kernels = {}
+    for name, (ms, n) in stages.items():
+        if n == 0:
+            continue
+        per = ms / n
+        k = {"launches": n, "ms_per_launch": per, "share_of_step": ms / ms_total}
+        if name in flops_per_launch:
+            k["tflops"] = flops_per_launch[name] / per / 1e9
+        elif name == "layernorm":
+            k["gbs"] = M * d * 6.0 / per / 1e6
+        kernels[name] = k
+    dominant = max((n for n in kernels if n in flops_per_launch), key=lambda n: stages[n][0])
+    tensor_peak = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(f"{dominant}:{args.workload}:B{B}")
+    roofline = {
+        "kernel": dominant, "bound": "tensor", "achieved": kernels[dominant]["tflops"], "peak": tensor_peak,
+        "unit": "TFLOP/s", "frac": kernels[dominant]["tflops"] / tensor_peak, "traffic": traffic,
+        "peak_source": f"{peak_src} sustained bf16 matmul (kernel timed inside a long step)",
+        "algorithmic_flops_per_launch": flops_per_launch[dominant],
+    }
+    fe_med = statistics.median(fe_ms)
+    fe_bytes = B * (N_SAMPLES * 4 + cfg.num_mel_bins * 3000 * 4)
+    frontend = {"bound": "hbm", "achieved": fe_bytes / fe_med / 1e6, "peak": float(peaks["hbm_gbs"]), "unit": "GB/s",
+                "frac": fe_bytes / fe_med / 1e6 / float(peaks["hbm_gbs"]), "ms_per_launch_group": fe_med,
+                "algorithmic_bytes_per_chunk": N_SAMPLES * 4 + cfg.num_mel_bins * 3000 * 4,
+                "note": "3 launches (fill, frames, finalize); also writes the bf16 time-major copy for the stem"}
+    enc_flops = cfg.flops_per_chunk() * B * n_gpus * args.steps
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                "h2d_bytes_per_step": int(host_pcm.numel() * 4) * n_gpus,
+                "d2h_bytes_per_step": int(host_out.numel() * 2) * n_gpus},
+        "gpu_launches": args.steps * (3 + enc.launches_per_forward - 1),
+        "clocks": clocks, "roofline": roofline, "frontend_roofline": frontend,
+        "encoder_tflops_whole_step": enc_flops / (ms_total / 1e3) / 1e12 / n_gpus,
+        "kernels": kernels,
+    }
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(args.workload)
+        sample_pcm = host_pcm[: args.ref_chunks].numpy()
+        ref.step(sample_pcm[:1])
+        secs = ref.step(sample_pcm)
+        line["cpu_baseline"] = {
+            "value": args.ref_chunks * CHUNK_SECONDS / secs, "unit": UNIT, "cores": ref.cores, "kind": ref.kind,
+            "sample": f"first {args.ref_chunks} chunk(s) of the same batch, one pass after a 1-chunk warm-up; HF numpy "
+                      f"log-mel + {'HF' if ref.kind == 'reference' else 'oracle-port'} fp32 encoder "
+                      "(the reference's CTranslate2 CPU encoder is not installable offline)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="large-v3", choices=["tiny", "base", "small", "medium", "large-v2", "large-v3"])
+    ap.add_argument("--batch", type=int, default=256, help="30 s chunks per GPU per step")
+    ap.add_argument("--ref-chunks", type=int, default=2, help="chunks per CPU reference step / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    return run_reference(args) if args.impl == "reference" else run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

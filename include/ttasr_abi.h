@@ -122,6 +122,14 @@ TTASR_API int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_
                           void* stream);
 /* number of kernel launches one forward of `batch` chunks enqueues (bench.py's gpu_launches accounting) */
 TTASR_API int ttasr_encoder_launch_count(const ttasr_encoder_t* h, int64_t* out);
+/* Optional per-stage timing (CUDA events recorded around every launch of ttasr_encoder_forward on its stream).
+ * Off by default; enabling it makes the handle single-threaded.  ttasr_encoder_profile_read waits for the recorded
+ * events and returns accumulated milliseconds and launch counts per stage kind (TTASR_PROFILE_KINDS entries:
+ * see ttasr_encoder_profile_kind_name). */
+#define TTASR_PROFILE_KINDS 9
+TTASR_API int ttasr_encoder_profile_enable(ttasr_encoder_t* h, int on);
+TTASR_API int ttasr_encoder_profile_read(ttasr_encoder_t* h, double* ms_by_kind, int64_t* launches_by_kind, int reset);
+TTASR_API const char* ttasr_encoder_profile_kind_name(int kind);
 TTASR_API void ttasr_encoder_destroy(ttasr_encoder_t* h);
 
 /* ------------------------------------------------------------------ single ops (parity tests / profiling) -----

@@ -286,15 +286,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 
 // GELU(x) = x * Phi(x), exact-erf form (HF ACT2FN["gelu"]).  erf via Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, far below the bf16 output rounding), 2 MUFU + ~12 FMA-pipe ops.
+// (|abs err| <= 1.5e-7 + approx-unit error ~1e-6, far below the bf16 output rounding): 2 MUFU + ~12 FMA-pipe ops,
+// branch-free (the IEEE __frcp_rn / expf forms compile to a slow-path CALL per element and serialise the epilogue).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));  // one MUFU.RCP, no IEEE slow path / branches
+  return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * __expf(-z * z);  // 1 - erf(z)
+  const float e = p * t * ex2_approx(-1.4426950408889634f * z * z);  // 1 - erf(z)
   const float half_erfc = 0.5f * e;        // Phi(-|x|)
   const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
   return x * phi;

@@ -215,7 +215,29 @@ struct LayerDev {
   const __nv_bfloat16 *wqkv, *wo, *w1, *w2;
 };
 
+enum ProfileKind { kProfPrep = 0, kProfConv1, kProfConv2, kProfLayerNorm, kProfQkv, kProfAttention, kProfOutProj,
+                   kProfFc1, kProfFc2, kProfKinds };
+static_assert(kProfKinds == TTASR_PROFILE_KINDS, "profile kinds out of sync with the header");
+const char* const kProfNames[kProfKinds] = {"feats_to_time_major", "conv1_gemm", "conv2_gemm", "layernorm", "qkv_gemm",
+                                            "attention", "out_proj_gemm", "fc1_gemm", "fc2_gemm"};
+
+struct ProfileState {
+  bool on = false;
+  struct Span { int kind; cudaEvent_t a, b; };
+  std::vector<Span> pending;
+  std::vector<cudaEvent_t> pool;
+  double ms[kProfKinds] = {0};
+  int64_t launches[kProfKinds] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+
 struct ttasr_encoder {
+  mutable ProfileState prof;
   int device = 0, num_sms = 0;
   ttasr_encoder_cfg cfg{};
   int c1_pad = 128;        // conv1 input channels padded per tap
@@ -387,10 +409,26 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
   const int B = static_cast<int>(batch);
   const char* why = nullptr;
   cudaError_t e;
-#define GEMM_TRY(call, name)                                                                                      \
+  ProfileState& prof = h->prof;
+  ProfileState::Span span{};
+  auto prof_begin = [&](int kind) {
+    if (!prof.on) return;
+    span.kind = kind;
+    span.a = prof.get();
+    span.b = prof.get();
+    cudaEventRecord(span.a, stream);
+  };
+  auto prof_end = [&]() {
+    if (!prof.on) return;
+    cudaEventRecord(span.b, stream);
+    prof.pending.push_back(span);
+  };
+#define GEMM_TRY(call, name, kind)                                                                                \
   do {                                                                                                            \
+    prof_begin(kind);                                                                                             \
     e = gemm_launch(call, h->num_sms, stream, &why);                                                              \
     if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: %s: %s", name, why ? why : cudaGetErrorString(e)); \
+    prof_end();                                                                                                   \
   } while (0)
 
   // ---- stem input as bf16 time-major
@@ -400,7 +438,9 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
     ld = c.n_mels;
     __nv_bfloat16* dst = qkv;  // scratch: dead before the first QKV GEMM
     dim3 grid((Tin + 31) / 32, (ld + 31) / 32, B);
+    prof_begin(kProfPrep);
     feats_to_tmajor_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(feats_dev), dst, c.n_mels, Tin, ld);
+    prof_end();
     ft = dst;
   } else if (feats_layout == TTASR_FEATS_BF16_TIME_MAJOR) {
     if (tmajor_ld < c.n_mels || tmajor_ld % 8 != 0) return fail(TTASR_E_SHAPE, "encoder_forward: tmajor_ld must be a multiple of 8 and >= n_mels");
@@ -416,7 +456,7 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
     g.a = ft; g.lda = ld; g.a_inner = c.n_mels; g.rows = Tin; g.nbatch = B;
     g.w = h->conv1_w; g.n = d; g.kb_per_tap = h->c1_pad / 64; g.k_blocks = 3 * g.kb_per_tap;
     g.bias = h->conv1_b; g.act = 1; g.out = c1; g.out_f32 = 0;
-    GEMM_TRY(g, "conv1");
+    GEMM_TRY(g, "conv1", kProfConv1);
   }
   {
     GemmCall g;
@@ -424,54 +464,96 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
     g.a = c1; g.lda = d; g.a_inner = d; g.rows = T; g.nbatch = B;
     g.w = h->conv2_w; g.n = d; g.kb_per_tap = d / 64; g.k_blocks = 3 * g.kb_per_tap;
     g.bias = h->conv2_b; g.act = 1; g.addend = h->pos; g.addend_bcast = 1; g.out = x; g.out_f32 = 1;
-    GEMM_TRY(g, "conv2");
+    GEMM_TRY(g, "conv2", kProfConv2);
   }
   const long long M = static_cast<long long>(B) * T;
   for (int i = 0; i < c.n_layers; ++i) {
     const LayerDev& l = h->layers[i];
+    prof_begin(kProfLayerNorm);
     e = layernorm_launch(x, l.ln1_g, l.ln1_b, hbuf, M, d, 0, stream);
+    prof_end();
     if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d ln1: %s", i, cudaGetErrorString(e));
     {
       GemmCall g;
       g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.wqkv; g.n = 3 * d; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.bqkv; g.out = qkv;
-      GEMM_TRY(g, "qkv");
+      GEMM_TRY(g, "qkv", kProfQkv);
     }
+    prof_begin(kProfAttention);
     e = attention_launch(qkv, hbuf, B, T, c.n_heads, h->num_sms, stream, &why);
+    prof_end();
     if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d attention: %s", i, why ? why : cudaGetErrorString(e));
     {
       GemmCall g;
       g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.wo; g.n = d; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.bo; g.addend = x; g.out = x; g.out_f32 = 1;
-      GEMM_TRY(g, "out_proj");
+      GEMM_TRY(g, "out_proj", kProfOutProj);
     }
+    prof_begin(kProfLayerNorm);
     e = layernorm_launch(x, l.ln2_g, l.ln2_b, hbuf, M, d, 0, stream);
+    prof_end();
     if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d ln2: %s", i, cudaGetErrorString(e));
     {
       GemmCall g;
       g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.w1; g.n = f; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.b1; g.act = 1; g.out = ffn;
-      GEMM_TRY(g, "fc1");
+      GEMM_TRY(g, "fc1", kProfFc1);
     }
     {
       GemmCall g;
       g.a = ffn; g.lda = f; g.a_inner = f; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.w2; g.n = d; g.k_blocks = f / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.b2; g.addend = x; g.out = x; g.out_f32 = 1;
-      GEMM_TRY(g, "fc2");
+      GEMM_TRY(g, "fc2", kProfFc2);
     }
   }
+  prof_begin(kProfLayerNorm);
   e = layernorm_launch(x, h->lnp_g, h->lnp_b, out_dev, M, d, out_dtype == TTASR_OUT_F32, stream);
+  prof_end();
   if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: final layer norm: %s", cudaGetErrorString(e));
 #undef GEMM_TRY
   return TTASR_OK;
 }
 
+int ttasr_encoder_profile_enable(ttasr_encoder_t* h, int on) {
+  if (!h) return fail(TTASR_E_ARG, "encoder_profile_enable: null handle");
+  h->prof.on = on != 0;
+  return TTASR_OK;
+}
+
+int ttasr_encoder_profile_read(ttasr_encoder_t* h, double* ms_by_kind, int64_t* launches_by_kind, int reset) {
+  if (!h || !ms_by_kind || !launches_by_kind) return fail(TTASR_E_ARG, "encoder_profile_read: null argument");
+  ProfileState& p = h->prof;
+  for (auto& sp : p.pending) {
+    cudaError_t e = cudaEventSynchronize(sp.b);
+    float ms = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.a, sp.b);
+    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_profile_read: %s", cudaGetErrorString(e));
+    p.ms[sp.kind] += ms;
+    p.launches[sp.kind] += 1;
+    p.pool.push_back(sp.a);
+    p.pool.push_back(sp.b);
+  }
+  p.pending.clear();
+  for (int k = 0; k < kProfKinds; ++k) {
+    ms_by_kind[k] = p.ms[k];
+    launches_by_kind[k] = p.launches[k];
+    if (reset) { p.ms[k] = 0; p.launches[k] = 0; }
+  }
+  return TTASR_OK;
+}
+
+const char* ttasr_encoder_profile_kind_name(int kind) {
+  return (kind >= 0 && kind < kProfKinds) ? kProfNames[kind] : "";
+}
+
 void ttasr_encoder_destroy(ttasr_encoder_t* h) {
   if (!h) return;
+  for (auto& sp : h->prof.pending) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+  for (auto e : h->prof.pool) cudaEventDestroy(e);
   cudaFree(h->arena);
   delete h;
 }

@@ -12,6 +12,7 @@ TTASR_OK = 0
 PCM_F32, PCM_I16 = 0, 1
 FEATS_F32_MEL_MAJOR, FEATS_BF16_TIME_MAJOR = 0, 1
 OUT_BF16, OUT_F32 = 0, 1
+PROFILE_KINDS = 9
 ERROR_NAMES = {-1: "TTASR_E_ARG", -2: "TTASR_E_SHAPE", -3: "TTASR_E_ARCH", -4: "TTASR_E_CUDA", -5: "TTASR_E_NOMEM"}
 
 
@@ -53,6 +54,9 @@ PROTOTYPES = {
     "ttasr_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_size_t,
                                         C.c_void_p, C.c_int, C.c_void_p]),
     "ttasr_encoder_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "ttasr_encoder_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "ttasr_encoder_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "ttasr_encoder_profile_kind_name": (C.c_char_p, [C.c_int]),
     "ttasr_encoder_destroy": (None, [C.c_void_p]),
     "ttasr_op_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                 C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -148,6 +148,18 @@ class B200WhisperEncoder:
         enc = model.get_encoder() if hasattr(model, "get_encoder") else model
         return cls(EncoderConfig.from_any(enc.config), enc.state_dict(), device=device)
 
+    # ------------------------------------------------------------------ per-stage timing (bench / profiling)
+    def profile(self, on: bool = True) -> None:
+        _lib.check(_lib.lib().ttasr_encoder_profile_enable(self._handle, 1 if on else 0))
+
+    def profile_read(self, reset: bool = True) -> dict:
+        """{stage name: (total ms, launches)} accumulated since the last reset; waits for the recorded events."""
+        ms = (C.c_double * _lib.PROFILE_KINDS)()
+        n = (C.c_int64 * _lib.PROFILE_KINDS)()
+        _lib.check(_lib.lib().ttasr_encoder_profile_read(self._handle, ms, n, 1 if reset else 0))
+        names = [_lib.lib().ttasr_encoder_profile_kind_name(k).decode() for k in range(_lib.PROFILE_KINDS)]
+        return {names[k]: (float(ms[k]), int(n[k])) for k in range(_lib.PROFILE_KINDS)}
+
     # ------------------------------------------------------------------ forward
     def workspace_bytes(self, batch: int) -> int:
         n = C.c_size_t()

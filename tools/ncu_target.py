@@ -1,0 +1,56 @@
+"""Small, fixed workloads for `ncu --set full` captures of one kernel family at a time (large-v3 shapes, B chunks).
+    python tools/ncu_target.py {gemm_fc1|gemm_fc2|gemm_qkv|gemm_out|attention|frontend|layernorm|encoder} [B]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "taiwan-tongues-asr-ce_b200"))
+import torch  # noqa: E402
+
+from ttasr import _lib as L  # noqa: E402
+
+
+def main():
+    what = sys.argv[1]
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    dev = torch.device("cuda", 0)
+    lib = L.lib()
+    st = int(torch.cuda.current_stream().cuda_stream)
+    M = 1500 * B
+    reps = 4
+    if what.startswith("gemm_"):
+        N, K, act, f32, add = {"gemm_fc1": (5120, 1280, 1, 0, 0), "gemm_fc2": (1280, 5120, 0, 1, 1),
+                               "gemm_qkv": (3840, 1280, 0, 0, 0), "gemm_out": (1280, 1280, 0, 1, 1)}[what]
+        a = torch.randn((M, K), device=dev).to(torch.bfloat16)
+        w = (torch.randn((N, K), device=dev) * K ** -0.5).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        o = torch.zeros((M, N), device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+        for _ in range(reps):
+            L.check(lib.ttasr_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), o.data_ptr() if add else None,
+                                      o.data_ptr(), M, N, K, act, f32, 0, st))
+    elif what == "attention":
+        H, T = 20, 1500
+        qkv = torch.randn((B, T, 3 * 64 * H), device=dev).to(torch.bfloat16)
+        o = torch.empty((B, T, 64 * H), device=dev, dtype=torch.bfloat16)
+        for _ in range(reps):
+            L.check(lib.ttasr_op_attention(qkv.data_ptr(), o.data_ptr(), B, T, H, st))
+    elif what == "frontend":
+        from ttasr import B200WhisperFeatureExtractor
+        fe = B200WhisperFeatureExtractor(feature_size=128)
+        pcm = (0.1 * torch.randn((max(B, 64), 480000), device=dev)).clamp_(-1, 1)
+        for _ in range(reps):
+            fe.extract(pcm, return_time_major=True)
+    elif what == "layernorm":
+        x = torch.randn((M, 1280), device=dev)
+        g = torch.ones(1280, device=dev)
+        y = torch.empty((M, 1280), device=dev, dtype=torch.bfloat16)
+        for _ in range(reps):
+            L.check(lib.ttasr_op_layernorm(x.data_ptr(), g.data_ptr(), g.data_ptr(), y.data_ptr(), M, 1280, 0, st))
+    else:
+        raise SystemExit(f"unknown target {what}")
+    torch.cuda.synchronize()
+
+
+if __name__ == "__main__":
+    main()
