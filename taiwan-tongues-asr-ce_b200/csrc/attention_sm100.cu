@@ -8,9 +8,13 @@
 //   warp 1      MMA issuer   : S_t = Q_t K^T (tcgen05.mma SS, 128x128x64, fp32 in TMEM);
 //                              O_t += P_t V (tcgen05.mma TS: P read from TMEM, V as an MN-major smem operand)
 //   warp 2      TMEM allocator (512 columns: S0 S1 | P0 P1 (bf16 pairs) | O0 O1)
-//   warps 4-7 / 8-11  softmax of tile 0 / 1, one thread per query row: online max with lazy rescale of O
-//                              (only when the running max grows by > 2^8), exp2 on pre-scaled logits, fp32 row sums,
-//                              P written back to TMEM as packed bf16; final O / l -> bf16 -> smem -> TMA store.
+//   warps 4-11  softmax: all eight warps walk the tiles in ONE alternating sequence (tile 0, tile 1, tile 0, ...), two
+//                              threads per query row (key columns 0-63 / 64-127 of the S tile), so the exp pipe
+//                              is busy on tile t while the tensor pipe produces S / consumes P of tile 1-t.
+//                              Exponentials are taken speculatively against the current base while the tile's exact
+//                              row max is exchanged between the two half-row threads; only if it outgrew the base
+//                              by > 2^32 are O rescaled and the exponentials redone from registers.  exp2 on pre-scaled logits, fp32 row sums, P written back
+//                              to TMEM as packed bf16; final O / l -> bf16 -> smem -> TMA store.
 // The 1500 x 1500 score matrix never leaves the SM; keys beyond n_ctx in the last tile are masked to -inf.
 #include "attention_sm100.h"
 #include "gemm_sm100.h"  // encode_tmap
@@ -25,7 +29,7 @@ constexpr int kTileBytes = kTile * kHeadDim * 2;  // 16 KB
 constexpr int kKvStages = 4;
 constexpr int kAttnThreads = 384;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kRescaleThreshold = 8.0f;  // log2 units
+constexpr float kRescaleThreshold = 32.0f;  // log2 units: P stays <= 2^32 (bf16 range 2^127, O and l are fp32)
 
 // TMEM column map
 constexpr uint32_t kColS = 0;     // S0 at 0, S1 at 128
@@ -52,12 +56,46 @@ struct AttnSmem {
   unsigned long long kv_full[kKvStages], kv_free[kKvStages];
   unsigned long long s_full[2], p_ready[2], o_done[2];
   uint32_t tmem_ptr;
+  float xmax[2][2][kTile];     // [tile][half][row] half-row max of the current S tile (exchanged between the 2 threads of a row)
+  float xsum[2][2][kTile];     // [tile][half][row] half-row sums at the end of an item
 };
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// max over 32 fp32 values held in registers (columns col0 .. col0+31 of this thread's half row)
+template <bool MASKED>
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int col0, int valid) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    if (!MASKED || col0 + 2 * i < valid) m0 = fmaxf(m0, __uint_as_float(v[2 * i]));
+    if (!MASKED || col0 + 2 * i + 1 < valid) m1 = fmaxf(m1, __uint_as_float(v[2 * i + 1]));
+  }
+  return fmaxf(m0, m1);
+}
+
+// p_i = 2^(s_i*log2e - m_used) for 32 columns -> 16 packed bf16 pairs; returns the fp32 sum
+template <bool MASKED>
+__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], int col0, int valid, float m_used, uint32_t (&pk)[16]) {
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float x0 = __uint_as_float(v[2 * i]), x1 = __uint_as_float(v[2 * i + 1]);
+    if (MASKED) {
+      if (col0 + 2 * i >= valid) x0 = -INFINITY;
+      if (col0 + 2 * i + 1 >= valid) x1 = -INFINITY;
+    }
+    const float p0 = ex2(fmaf(x0, kLog2e, -m_used));
+    const float p1 = ex2(fmaf(x1, kLog2e, -m_used));
+    sum0 += p0;
+    sum1 += p1;
+    pk[i] = pack_bf16x2(p0, p1);
+  }
+  return sum0 + sum1;
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
@@ -82,7 +120,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&s.s_full[t]), 1);
-      mbar_init(smem_u32(&s.p_ready[t]), 4);
+      mbar_init(smem_u32(&s.p_ready[t]), 8);
       mbar_init(smem_u32(&s.o_done[t]), 1);
     }
     fence_mbar_init();
@@ -161,17 +199,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
             tc_fence_after();
           }
           for (int t = 0; t < 2; ++t) {
-            mbar_wait(smem_u32(&s.p_ready[t]), pphase[t]);  // softmax done: S_t free, P_t(j) in TMEM
+            mbar_wait(smem_u32(&s.p_ready[t]), pphase[t]);  // softmax of tile t done: S_t free, P_t(j) in TMEM
             pphase[t] ^= 1;
             tc_fence_after();
-            if (more) issue_s(t, stage);
             // O_t (+)= P_t V_j : V tile is [128 keys][64] row-major = MN-major B operand, 16 keys per MMA
             const uint64_t vdesc = umma_desc_sw128(smem_u32(&s.v[cur][0]), kTileBytes, 1024);
 #pragma unroll
             for (int k = 0; k < kTile / 16; ++k)
               umma_ts(tmem_base + kColO + t * kHeadDim, tmem_base + kColP + t * 64 + k * 8, vdesc + 128 * k, idesc_o,
                       (j | k) != 0 ? 1u : 0u);
-            umma_commit(smem_u32(&s.o_done[t]));
+            // next S_t after the PV: its completion (s_full) then also tells the softmax warps that P_t and O_t are
+            // free again; it is not needed before they finish tile 1-t, ~1000 cycles away
+            if (more) issue_s(t, stage);
+            else umma_commit(smem_u32(&s.o_done[t]));
           }
           umma_commit(smem_u32(&s.kv_free[cur]));  // every MMA that read stage `cur` has been issued
           if (more) {
@@ -183,104 +223,99 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== softmax + output, one thread per query row
-    const int t = (warp - 4) >> 2;          // query tile 0 / 1
+    // ===================================================== softmax + output, two threads per query row
+    const int half = (warp - 4) >> 2;       // key columns [64*half, 64*half+64) of every S tile; O columns [32*half, +32)
     const int wq = warp & 3;                // TMEM lane quarter
     const int row = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_base + kColS + t * kTile;
-    const uint32_t p_addr = tmem_base + lane_base + kColP + t * 64;
-    const uint32_t o_addr = tmem_base + lane_base + kColO + t * kHeadDim;
-    const uint32_t bar_id = 1 + t;
-    const bool leader = (wq == 0 && lane == 0);
-    uint32_t sphase = 0, ophase = 0;
-    const int last_valid = p.n_ctx - (p.kv_tiles - 1) * kTile;  // valid keys in the last KV tile
+    const bool leader = (warp == 4 && lane == 0);
+    constexpr uint32_t kSoftBar = 1;        // named barrier of the 256 softmax threads
+    constexpr uint32_t kPairBar = 2;        // +wq: named barrier of the two warps sharing a row quarter
+    uint32_t sphase[2] = {0, 0}, ophase[2] = {0, 0};
+    const int last_valid = p.n_ctx - (p.kv_tiles - 1) * kTile;                       // valid keys in the last KV tile
+    const int last_valid_h = min(max(last_valid - 64 * half, 0), 64);              // ... within this thread's half
+    const bool last_masked = last_valid < kTile;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, h, q0;
       item_coords(item, b, h, q0);
-      float m_used = -INFINITY;  // max the exponentials are taken against (log2 domain), lags the true max
-      float l = 0.f;
+      float m_used[2] = {0.f, 0.f};  // base of the exponentials (log2 domain); lags the true row max by <= 2^32
+      float l[2] = {0.f, 0.f};       // this half's row sum
       for (int j = 0; j < p.kv_tiles; ++j) {
-        mbar_wait(smem_u32(&s.s_full[t]), sphase);
-        sphase ^= 1;
-        tc_fence_after();
-        const int valid = (j == p.kv_tiles - 1) ? last_valid : kTile;
-        // pass 1: row max
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_addr + c * 32, v);
-          tmem_wait_ld();
+        const bool masked = last_masked && (j == p.kv_tiles - 1);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float x = (c * 32 + i < valid) ? __uint_as_float(v[i]) : -INFINITY;
-            mx = fmaxf(mx, x);
-          }
-        }
-        const float m_new = fmaxf(m_used, mx * kLog2e);
-        const bool grow = (m_new - m_used) > kRescaleThreshold;  // true on the first tile (m_used = -inf)
-        const bool any_grow = __any_sync(0xffffffffu, grow);
-        if (j > 0) {  // PV(j-1) must have consumed P and finished accumulating into O
-          mbar_wait(smem_u32(&s.o_done[t]), ophase);
-          ophase ^= 1;
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t s_addr = tmem_base + lane_base + kColS + t * kTile + half * 64;
+          const uint32_t p_addr = tmem_base + lane_base + kColP + t * 64 + half * 32;
+          const uint32_t o_addr = tmem_base + lane_base + kColO + t * kHeadDim + half * 32;
+          // S_t(j) complete; being issued after PV_t(j-1) it also means P_t is consumed and O_t is quiescent
+          mbar_wait(smem_u32(&s.s_full[t]), sphase[t]);
+          sphase[t] ^= 1;
           tc_fence_after();
-        }
-        if (any_grow) {
-          const float factor = (j > 0) ? ex2(m_used - m_new) : 0.f;
-          m_used = m_new;
-          if (j > 0) {
-            l *= factor;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-              uint32_t v[32];
-              tmem_ld_32x32(o_addr + c * 32, v);
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(s_addr, v0);
+          tmem_ld_32x32(s_addr + 32, v1);
+          tmem_wait_ld();
+          uint32_t pk0[16], pk1[16];
+          float lsum = 0.f;
+          if (j > 0) {  // speculate on the current base: the exponentials do not wait for this tile's max
+            lsum = masked ? chunk_exp<true>(v0, 0, last_valid_h, m_used[t], pk0) + chunk_exp<true>(v1, 32, last_valid_h, m_used[t], pk1)
+                          : chunk_exp<false>(v0, 0, 64, m_used[t], pk0) + chunk_exp<false>(v1, 32, 64, m_used[t], pk1);
+          }
+          // exact row max of this tile: own 64 columns from registers, the other 64 from the partner thread
+          const float own = masked ? fmaxf(chunk_max<true>(v0, 0, last_valid_h), chunk_max<true>(v1, 32, last_valid_h))
+                                   : fmaxf(chunk_max<false>(v0, 0, 64), chunk_max<false>(v1, 32, 64));
+          s.xmax[t][half][row] = own;
+          bar_sync(kPairBar + wq, 64);
+          const float m_tile = fmaxf(own, s.xmax[t][half ^ 1][row]) * kLog2e;
+          // first tile, or (rare) the max outgrew the base by > 2^32: move the base and redo the exponentials from the
+          // registers.  Both half-row warps see the same maxima, so they branch together.
+          const bool redo = (j == 0) || __any_sync(0xffffffffu, (m_tile - m_used[t]) > kRescaleThreshold);
+          if (redo) {
+            const float m_new = (j == 0) ? m_tile : fmaxf(m_used[t], m_tile);
+            if (j > 0) {
+              const float factor = ex2(m_used[t] - m_new);
+              l[t] *= factor;
+              uint32_t o[32];
+              tmem_ld_32x32(o_addr, o);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * factor);
-              tmem_st_32x32(o_addr + c * 32, v);
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st_32x32(o_addr, o);
             }
+            m_used[t] = m_new;
+            lsum = masked ? chunk_exp<true>(v0, 0, last_valid_h, m_new, pk0) + chunk_exp<true>(v1, 32, last_valid_h, m_new, pk1)
+                          : chunk_exp<false>(v0, 0, 64, m_new, pk0) + chunk_exp<false>(v1, 32, 64, m_new, pk1);
           }
+          l[t] += lsum;
+          tmem_st_32x16(p_addr, pk0);
+          tmem_st_32x16(p_addr + 16, pk1);
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&s.p_ready[t]));
         }
-        // pass 2: p = 2^(s*log2e - m_used), row sum, packed bf16 -> TMEM
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(s_addr + c * 32, v);
-          tmem_wait_ld();
-          uint32_t pk[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x0 = (c * 32 + 2 * i < valid) ? __uint_as_float(v[2 * i]) : -INFINITY;
-            const float x1 = (c * 32 + 2 * i + 1 < valid) ? __uint_as_float(v[2 * i + 1]) : -INFINITY;
-            const float p0 = ex2(fmaf(x0, kLog2e, -m_used));
-            const float p1 = ex2(fmaf(x1, kLog2e, -m_used));
-            l += p0 + p1;
-            pk[i] = pack_bf16x2(p0, p1);
-          }
-          tmem_st_32x16(p_addr + c * 16, pk);
-        }
-        tmem_wait_st();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&s.p_ready[t]));
       }
-      // ---- epilogue: O / l -> bf16 -> swizzled smem -> TMA store
-      mbar_wait(smem_u32(&s.o_done[t]), ophase);
-      ophase ^= 1;
+      // ---- epilogue: O / l -> bf16 -> swizzled smem -> TMA store (both tiles)
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        mbar_wait(smem_u32(&s.o_done[t]), ophase[t]);
+        ophase[t] ^= 1;
+        s.xsum[t][half][row] = l[t];
+      }
       tc_fence_after();
-      if (leader) tma_store_wait_read<0>();  // staging tile of the previous item has been read out
-      bar_sync(bar_id, 128);
-      const float inv = 1.0f / l;
-      const uint32_t o_row = smem_u32(&s.o[t][0]) + row * 128;
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      if (leader) tma_store_wait_read<0>();  // staging tiles of the previous item have been read out
+      bar_sync(kSoftBar, 256);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t o_addr = tmem_base + lane_base + kColO + t * kHeadDim + half * 32;
+        const float inv = 1.0f / (l[t] + s.xsum[t][half ^ 1][row]);
+        const uint32_t o_row = smem_u32(&s.o[t][0]) + row * 128;
         uint32_t v[32];
-        tmem_ld_32x32(o_addr + c * 32, v);
+        tmem_ld_32x32(o_addr, v);
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = c * 4 + q;  // 16-byte chunk = 8 channels
+          const int chunk = half * 4 + q;  // 16-byte chunk = 8 channels
           const uint32_t a0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
           const uint32_t a1 = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
           const uint32_t a2 = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
@@ -292,9 +327,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      bar_sync(bar_id, 128);
+      bar_sync(kSoftBar, 256);
       if (leader) {
-        tma_store_3d(&p.tm_out, smem_u32(&s.o[t][0]), h * kHeadDim, q0 + t * kTile, b);
+        tma_store_3d(&p.tm_out, smem_u32(&s.o[0][0]), h * kHeadDim, q0, b);
+        tma_store_3d(&p.tm_out, smem_u32(&s.o[1][0]), h * kHeadDim, q0 + kTile, b);
         tma_store_commit();
       }
     }

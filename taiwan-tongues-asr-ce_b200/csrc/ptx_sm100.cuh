@@ -9,9 +9,10 @@
 
 namespace ttasr {
 
-#ifndef TTASR_SPIN_LIMIT
-#define TTASR_SPIN_LIMIT (1u << 22)  // bounded mbarrier spins: a protocol bug traps instead of hanging the GPU
+#ifndef TTASR_WAIT_TIMEOUT_CYCLES
+#define TTASR_WAIT_TIMEOUT_CYCLES (4000000000ll)  // ~2 s: a protocol bug traps instead of hanging the GPU
 #endif
+#define TTASR_SUSPEND_HINT_NS 100000u  // mbarrier.try_wait may sleep this long; it still wakes on phase completion
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -63,31 +64,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred P;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, P;\n\t}\n"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(TTASR_SUSPEND_HINT_NS)
       : "memory");
   return ok != 0;
 }
+static __device__ __noinline__ void mbar_timeout_check(long long t0) {
+  if (clock64() - t0 > TTASR_WAIT_TIMEOUT_CYCLES) __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > TTASR_SPIN_LIMIT) __trap();
+    if ((++spins & 1023u) == 0) mbar_timeout_check(t0);
   }
 }
 // acquire at cluster scope: needed when the arrive came from the peer CTA's generic-proxy thread
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
   uint32_t spins = 0, ok = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(TTASR_SUSPEND_HINT_NS)
         : "memory");
-    if (!ok && ++spins > TTASR_SPIN_LIMIT) __trap();
+    if (!ok && (++spins & 1023u) == 0) mbar_timeout_check(t0);
   } while (!ok);
 }
 

@@ -31,7 +31,9 @@ def main():
                                       o.data_ptr(), M, N, K, act, f32, 0, st))
     elif what == "attention":
         H, T = 20, 1500
-        qkv = torch.randn((B, T, 3 * 64 * H), device=dev).to(torch.bfloat16)
+        qkv = torch.randn((B, T, 3 * 64 * H), device=dev)
+        qkv[..., : 64 * H] *= 0.125
+        qkv = qkv.to(torch.bfloat16)
         o = torch.empty((B, T, 64 * H), device=dev, dtype=torch.bfloat16)
         for _ in range(reps):
             L.check(lib.ttasr_op_attention(qkv.data_ptr(), o.data_ptr(), B, T, H, st))
