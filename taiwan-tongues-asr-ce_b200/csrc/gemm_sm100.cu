@@ -9,9 +9,12 @@
 //   warp 1  MMA issuer     : one elected thread, tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), M = 128 * CG, N = BN,
 //                            accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
 //                            overlaps the MMAs of tile i+1
-//   warp 2  TMEM allocator
-//   warps 4-7 epilogue     : tcgen05.ld -> bias / GELU / residual (addend tile prefetched by TMA into the same
-//                            swizzled staging slab) -> st.shared -> TMA store (clips the M tail)
+//   warp 2  TMEM allocator, then the output-store thread: waits for a finished staging slab, issues its TMA store
+//                            (clips the M tail) and recycles the slab when the store has read it
+//   warp 3  addend loader  : (residual / positional variants) TMA-prefetches the fp32 addend slabs into the staging
+//                            ring as far ahead as slabs are free, so DRAM latency is off the epilogue's path
+//   warps 4-11 epilogue    : two warpgroups taking alternate column slabs: tcgen05.ld -> bias / GELU / + addend ->
+//                            swizzled st.shared; they only ever wait on mbarriers, never on TMA bookkeeping
 // Tiles are walked n-fastest so the CTAs of a wave share a few A row-blocks and all of W in L2.
 #include "gemm_sm100.h"
 #include "ptx_sm100.cuh"
@@ -24,16 +27,16 @@ constexpr int kBM = 128;
 constexpr int kBK = 64;
 constexpr int kUmmaK = 16;
 constexpr int kSlabBytes = kBM * 128;  // staging slab: 128 rows x 128 B
-constexpr int kThreadsGemm = 256;
-constexpr int kEpiBarrier = 1;
+constexpr int kThreadsGemm = 384;
 constexpr int kMaxSmem = 232448;  // 227 KB
 
-template <int BN, int CG>
+template <int BN, int CG, bool HAS_ADD>
 struct Cfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBRows = BN / CG;
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  // staging ring: deeper for the addend variants (each slab is in flight from its TMA prefetch until its store is read)
   static constexpr int kNBuf = 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kStagesRaw = (kMaxSmem - 1024 - kBarBytes - kNBuf * kSlabBytes) / kStageBytes;
@@ -77,11 +80,13 @@ __device__ __forceinline__ float apply_act(float x) {
 
 template <int BN, int CG, int ACT, bool HAS_ADD, bool OUT_F32>
 __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, HAS_ADD>;
   constexpr int kStages = C::kStages;
   constexpr int kNBuf = C::kNBuf;
   constexpr int kSlabCols = OUT_F32 ? 32 : 64;
   constexpr int kNSlab = BN / kSlabCols;
+  static_assert(kNSlab % 2 == 0, "two epilogue warpgroups take alternate slabs");
+  static_assert(OUT_F32 || !HAS_ADD, "bf16 output with an addend is not instantiated");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = smem_u32(smem_raw);
@@ -94,8 +99,10 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
   auto empty_bar = [&](int i) { return sBar + 8u * (kStages + i); };
   auto tfull_bar = [&](int i) { return sBar + 8u * (2 * kStages + i); };
   auto tempty_bar = [&](int i) { return sBar + 8u * (2 * kStages + 2 + i); };
-  auto add_bar = [&](int i) { return sBar + 8u * (2 * kStages + 4 + i); };
-  const uint32_t tmem_slot = sBar + 8u * (2 * kStages + 4 + kNBuf);
+  auto add_full = [&](int i) { return sBar + 8u * (2 * kStages + 4 + i); };
+  auto out_ready = [&](int i) { return sBar + 8u * (2 * kStages + 4 + kNBuf + i); };
+  auto buf_free = [&](int i) { return sBar + 8u * (2 * kStages + 4 + 2 * kNBuf + i); };
+  const uint32_t tmem_slot = sBar + 8u * (2 * kStages + 4 + 3 * kNBuf);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem0));
 
   const int warp = threadIdx.x >> 5;
@@ -117,9 +124,13 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4 * CG);
+      mbar_init(tempty_bar(i), 8 * CG);
     }
-    for (int i = 0; i < kNBuf; ++i) mbar_init(add_bar(i), 1);
+    for (int i = 0; i < kNBuf; ++i) {
+      mbar_init(add_full(i), 1);
+      mbar_init(out_ready(i), 4);
+      mbar_init(buf_free(i), 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -202,58 +213,78 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
-    // ===================================================== epilogue
-    const int ew = warp - 4;
-    const int row = ew * 32 + lane;
-    const bool e0 = (threadIdx.x == 128);
-    const uint32_t lane_base = static_cast<uint32_t>(ew * 32) << 16;
+  } else if (warp == 2) {
+    // ===================================================== output-store thread
+    if (lane == 0) {
+      uint32_t q = 0;  // running slab counter -> staging buffer q % kNBuf, use number q / kNBuf
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        int b, t0, n0;
+        tile_coords(tile, b, t0, n0);
+        for (int s = 0; s < kNSlab; ++s, ++q) {
+          const uint32_t buf = q % kNBuf;
+          mbar_wait(out_ready(buf), (q / kNBuf) & 1);
+          tma_store_3d(&p.tm_out, sE + buf * kSlabBytes, n0 + s * kSlabCols, t0, b);
+          tma_store_commit();
+          if (q > 0) {  // the previous store has finished reading its slab: recycle it
+            tma_store_wait_read<1>();
+            mbar_arrive(buf_free((q - 1) % kNBuf));
+          }
+        }
+      }
+      tma_store_wait<0>();
+    }
+  } else if (warp == 3) {
+    // ===================================================== addend loader
+    if (HAS_ADD && lane == 0) {
+      uint32_t q = 0;
+      for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+        int b, t0, n0;
+        tile_coords(tile, b, t0, n0);
+        const int add_b = p.add_bcast ? 0 : b;
+        for (int s = 0; s < kNSlab; ++s, ++q) {
+          const uint32_t buf = q % kNBuf;
+          mbar_wait(buf_free(buf), ((q / kNBuf) & 1) ^ 1);
+          mbar_arrive_expect_tx(add_full(buf), kSlabBytes);
+          tma_load_3d(sE + buf * kSlabBytes, &p.tm_add, add_full(buf), n0 + s * kSlabCols, t0, add_b);
+        }
+      }
+    }
+  } else {
+    // ===================================================== epilogue: two warpgroups, alternate slabs
+    const int wg = (warp - 4) >> 2;
+    const int wq = warp & 3;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
     const uint32_t row_off = row * 128;
     const uint32_t swz = row & 7;
     int as = 0;
     uint32_t aphase = 0;
-    uint32_t g = 0;  // running slab counter -> staging buffer g % kNBuf
-    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+    uint32_t q0 = 0;  // running slab counter at the start of the tile
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters, q0 += kNSlab) {
       int b, t0, n0;
       tile_coords(tile, b, t0, n0);
-      const int add_b = p.add_bcast ? 0 : b;
-      if (HAS_ADD && e0) {
-        tma_store_wait_read<kNBuf - 1>();
-        const uint32_t bar = add_bar(g % kNBuf);
-        mbar_arrive_expect_tx(bar, kSlabBytes);
-        tma_load_3d(sE + (g % kNBuf) * kSlabBytes, &p.tm_add, bar, n0, t0, add_b);
-      }
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t acc_addr = tmem_base + lane_base + as * BN;
 #pragma unroll 1
-      for (int s = 0; s < kNSlab; ++s, ++g) {
-        const uint32_t buf = g % kNBuf;
+      for (int s = wg; s < kNSlab; s += 2) {
+        const uint32_t q = q0 + s;
+        const uint32_t buf = q % kNBuf;
+        const uint32_t use = (q / kNBuf) & 1;
         const uint32_t slab = sE + buf * kSlabBytes;
-        if (e0) {
-          if (HAS_ADD) {
-            if (s + 1 < kNSlab) {
-              tma_store_wait_read<kNBuf - 2>();
-              const uint32_t nb = (g + 1) % kNBuf;
-              mbar_arrive_expect_tx(add_bar(nb), kSlabBytes);
-              tma_load_3d(sE + nb * kSlabBytes, &p.tm_add, add_bar(nb), n0 + (s + 1) * kSlabCols, t0, add_b);
-            }
-          } else {
-            tma_store_wait_read<kNBuf - 1>();
-          }
-        }
-        if (!HAS_ADD) bar_sync(kEpiBarrier, 128);  // slab `buf` is free again
+        const bool last = (s + 2 >= kNSlab);
 
         if constexpr (OUT_F32) {
           uint32_t acc[32];
           tmem_ld_32x32(acc_addr + s * 32, acc);
           tmem_wait_ld();
-          if (s == kNSlab - 1) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+          if (last) {  // this warp has read all of its accumulator columns: hand the TMEM stage back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
           }
-          if (HAS_ADD) mbar_wait(add_bar(buf), (g / kNBuf) & 1);
+          if (HAS_ADD) mbar_wait(add_full(buf), use);         // addend slab landed (prefetched by warp 3)
+          else mbar_wait(buf_free(buf), use ^ 1);             // slab recycled by the store thread
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 32);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -272,16 +303,16 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
             sts128(addr, v);
           }
         } else {
-          static_assert(OUT_F32 || !HAS_ADD, "bf16 output with an addend is not instantiated");
           uint32_t acc0[32], acc1[32];
           tmem_ld_32x32(acc_addr + s * 64, acc0);
           tmem_ld_32x32(acc_addr + s * 64 + 32, acc1);
           tmem_wait_ld();
-          if (s == kNSlab - 1) {
+          if (last) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
           }
+          mbar_wait(buf_free(buf), use ^ 1);
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 64);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 16-byte chunk = 8 bf16 columns
@@ -299,16 +330,12 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
                     pack_bf16x2(v6, v7));
           }
         }
-        fence_proxy_async_smem();
-        bar_sync(kEpiBarrier, 128);
-        if (e0) {
-          tma_store_3d(&p.tm_out, slab, n0 + s * kSlabCols, t0, b);
-          tma_store_commit();
-        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if (lane == 0) mbar_arrive(out_ready(buf));
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if (e0) tma_store_wait<0>();
   }
 
   // ---- teardown
@@ -335,7 +362,7 @@ EncodeTiledFn get_encode_fn() {
 
 template <int BN, int CG, int ACT, bool HAS_ADD, bool OUT_F32>
 cudaError_t launch_variant(const GemmParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<BN, CG>;
+  using C = Cfg<BN, CG, HAS_ADD>;
   auto kern = gemm_kernel<BN, CG, ACT, HAS_ADD, OUT_F32>;
   static bool attr_done = false;
   if (!attr_done) {
