@@ -280,7 +280,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # control plane only (barrier + max-over-ranks of the timings): the data path has no collective, so a CPU
+        # (gloo) group is all that is needed — and NCCL's banner would pollute the one-JSON-line stdout contract
+        dist.init_process_group("gloo")
     n_gpus = world
 
     cfg = arch_table(args.workload)

@@ -42,18 +42,21 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = True) -> str:
+def build(force: bool = False, verbose: bool = True, defines: tuple = (), out: str | None = None) -> str:
+    """defines / out: build an experiment variant (-D...) into another file without touching the default library."""
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
-    stamp = os.path.join(OBJDIR, "digest.txt")
-    digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == digest:
-        return LIB
+    objdir = OBJDIR if not out else OBJDIR + "_" + os.path.basename(out)
+    os.makedirs(objdir, exist_ok=True)
+    lib = out or LIB
+    stamp = os.path.join(objdir, "digest.txt")
+    digest = _digest() + "|" + " ".join(defines)
+    if not force and os.path.exists(lib) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return lib
     nvcc = _nvcc()
 
     def compile_one(src: str) -> str:
-        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", CSRC, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -61,7 +64,7 @@ def build(force: bool = False, verbose: bool = True) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
+    cmd = [nvcc, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a",
            "-Xcompiler", "-fPIC", "-lpthread", "-ldl", "-lrt"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
@@ -69,9 +72,11 @@ def build(force: bool = False, verbose: bool = True) -> str:
     with open(stamp, "w") as f:
         f.write(digest)
     if verbose:
-        print(f"built {LIB} ({os.path.getsize(LIB)} bytes)")
-    return LIB
+        print(f"built {lib} ({os.path.getsize(lib)} bytes)")
+    return lib
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    _defs = tuple(a[2:] for a in sys.argv[1:] if a.startswith("-D"))
+    _out = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")), None)
+    build(force="--force" in sys.argv, defines=_defs, out=_out)

@@ -8,13 +8,13 @@
 //   warp 1      MMA issuer   : S_t = Q_t K^T (tcgen05.mma SS, 128x128x64, fp32 in TMEM);
 //                              O_t += P_t V (tcgen05.mma TS: P read from TMEM, V as an MN-major smem operand)
 //   warp 2      TMEM allocator (512 columns: S0 S1 | P0 P1 (bf16 pairs) | O0 O1)
-//   warps 4-11  softmax: all eight warps walk the tiles in ONE alternating sequence (tile 0, tile 1, tile 0, ...), two
-//                              threads per query row (key columns 0-63 / 64-127 of the S tile), so the exp pipe
-//                              is busy on tile t while the tensor pipe produces S / consumes P of tile 1-t.
-//                              Exponentials are taken speculatively against the current base while the tile's exact
-//                              row max is exchanged between the two half-row threads; only if it outgrew the base
-//                              by > 2^32 are O rescaled and the exponentials redone from registers.  exp2 on pre-scaled logits, fp32 row sums, P written back
-//                              to TMEM as packed bf16; final O / l -> bf16 -> smem -> TMA store.
+//   warps 4-7 / 8-11  softmax of query tile 0 / 1, one thread per query row.  The exp sweeps of the two warpgroups
+//                              are forced into anti-phase by a token (two named barriers) so the 16-op/clk exp pipe
+//                              always has exactly one warpgroup feeding it, while the other one waits for its next
+//                              S tile, loads it from TMEM and takes the row max (thread-local, exact).  O is
+//                              rescaled only when the max outgrows the exponent base by > 2^32.  exp2 on
+//                              pre-scaled logits, fp32 row sums, P written back to TMEM as packed bf16; final
+//                              O / l -> bf16 -> smem -> TMA store.
 // The 1500 x 1500 score matrix never leaves the SM; keys beyond n_ctx in the last tile are masked to -inf.
 #include "attention_sm100.h"
 #include "gemm_sm100.h"  // encode_tmap
@@ -30,6 +30,10 @@ constexpr int kKvStages = 4;
 constexpr int kAttnThreads = 384;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr bool kEmulateQuarter = false;  // every 4th exponential on the FMA pipe instead of MUFU: measured slower (0.79 vs 0.73 ms)
+#ifndef TTASR_ATTN_PRETOKEN
+#define TTASR_ATTN_PRETOKEN 1
+#endif
+constexpr int kPreTokenChunks = TTASR_ATTN_PRETOKEN;  // quarters of the exp sweep done outside the token
 constexpr float kRescaleThreshold = 32.0f;  // log2 units: P stays <= 2^32 (bf16 range 2^127, O and l are fp32)
 
 // TMEM column map
@@ -55,10 +59,8 @@ struct AttnSmem {
   uint8_t o[2][kTileBytes];
   unsigned long long q_full, q_free;
   unsigned long long kv_full[kKvStages], kv_free[kKvStages];
-  unsigned long long s_full[2], p_ready[2], o_done[2];
+  unsigned long long s_full[2], s_free[2], p_ready[2], o_done[2];
   uint32_t tmem_ptr;
-  float xmax[2][2][kTile];     // [tile][half][row] half-row max of the current S tile (exchanged between the 2 threads of a row)
-  float xsum[2][2][kTile];     // [tile][half][row] half-row sums at the end of an item
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -134,7 +136,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&s.s_full[t]), 1);
-      mbar_init(smem_u32(&s.p_ready[t]), 8);
+      mbar_init(smem_u32(&s.s_free[t]), 4);
+      mbar_init(smem_u32(&s.p_ready[t]), 4);
       mbar_init(smem_u32(&s.o_done[t]), 1);
     }
     fence_mbar_init();
@@ -196,6 +199,27 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           umma_ss<1>(tmem_base + kColS + t * kTile, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
         umma_commit(smem_u32(&s.s_full[t]));
       };
+      uint32_t fphase[2] = {0, 0};
+      // O_t (+)= P_t V : V tile is [128 keys][64] row-major = MN-major B operand, 16 keys per MMA
+      auto issue_pv = [&](int t, int st, bool first, bool last) {
+        const uint64_t vdesc = umma_desc_sw128(smem_u32(&s.v[st][0]), kTileBytes, 1024);
+#pragma unroll
+        for (int k = 0; k < kTile / 16; ++k)
+          umma_ts(tmem_base + kColO + t * kHeadDim, tmem_base + kColP + t * 64 + k * 8, vdesc + 128 * k, idesc_o,
+                  (first && k == 0) ? 0u : 1u);
+        umma_commit(smem_u32(&s.o_done[t]));  // per-PV completion: P_t consumed, O_t quiescent
+        (void)last;
+      };
+      auto wait_p = [&](int t) {
+        mbar_wait(smem_u32(&s.p_ready[t]), pphase[t]);
+        pphase[t] ^= 1;
+        tc_fence_after();
+      };
+      auto wait_sfree = [&](int t) {
+        mbar_wait(smem_u32(&s.s_free[t]), fphase[t]);
+        fphase[t] ^= 1;
+        tc_fence_after();
+      };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         mbar_wait(smem_u32(&s.q_full), qphase);
         qphase ^= 1;
@@ -204,132 +228,148 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         issue_s(0, stage);
         issue_s(1, stage);
         if (p.kv_tiles == 1) umma_commit(smem_u32(&s.q_free));
-        int cur = stage;
+        int cur = stage;   // stage of KV tile j
+        int prev = stage;  // stage of KV tile j-1
         if (++stage == kKvStages) { stage = 0; phase ^= 1; }
+        // Steady-state order of events in anti-phase operation (warpgroup 0 sweeps while warpgroup 1 loads its S):
+        //   S0(j) read out -> S0(j+1);  P1(j-1) ready -> PV1(j-1);  S1(j) read out -> S1(j+1);  P0(j) ready -> PV0(j)
+        // The next S tile of a warpgroup is thus produced a whole exp sweep before it is needed.
         for (int j = 0; j < p.kv_tiles; ++j) {
           const bool more = (j + 1 < p.kv_tiles);
           if (more) {
             mbar_wait(smem_u32(&s.kv_full[stage]), phase);
             tc_fence_after();
+            wait_sfree(0);
+            issue_s(0, stage);
+          } else {
+            wait_sfree(0);
           }
-          for (int t = 0; t < 2; ++t) {
-            mbar_wait(smem_u32(&s.p_ready[t]), pphase[t]);  // softmax of tile t done: S_t free, P_t(j) in TMEM
-            pphase[t] ^= 1;
-            tc_fence_after();
-            // O_t (+)= P_t V_j : V tile is [128 keys][64] row-major = MN-major B operand, 16 keys per MMA
-            const uint64_t vdesc = umma_desc_sw128(smem_u32(&s.v[cur][0]), kTileBytes, 1024);
-#pragma unroll
-            for (int k = 0; k < kTile / 16; ++k)
-              umma_ts(tmem_base + kColO + t * kHeadDim, tmem_base + kColP + t * 64 + k * 8, vdesc + 128 * k, idesc_o,
-                      (j | k) != 0 ? 1u : 0u);
-            // next S_t after the PV: its completion (s_full) then also tells the softmax warps that P_t and O_t are
-            // free again; it is not needed before they finish tile 1-t, ~1000 cycles away
-            if (more) issue_s(t, stage);
-            else umma_commit(smem_u32(&s.o_done[t]));
+          if (j > 0) {
+            wait_p(1);
+            issue_pv(1, prev, j == 1, false);
+            umma_commit(smem_u32(&s.kv_free[prev]));  // every MMA that read KV tile j-1 has been issued
           }
-          umma_commit(smem_u32(&s.kv_free[cur]));  // every MMA that read stage `cur` has been issued
           if (more) {
+            wait_sfree(1);
+            issue_s(1, stage);
             if (j + 2 == p.kv_tiles) umma_commit(smem_u32(&s.q_free));  // last S of the item issued
+          } else {
+            wait_sfree(1);
+          }
+          wait_p(0);
+          issue_pv(0, cur, j == 0, !more);
+          prev = cur;
+          if (more) {
             cur = stage;
             if (++stage == kKvStages) { stage = 0; phase ^= 1; }
           }
         }
+        wait_p(1);
+        issue_pv(1, prev, p.kv_tiles == 1, true);
+        umma_commit(smem_u32(&s.kv_free[prev]));
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== softmax + output, two threads per query row
-    const int half = (warp - 4) >> 2;       // key columns [64*half, 64*half+64) of every S tile; O columns [32*half, +32)
+    // ===================================================== softmax + output, one thread per query row
+    const int t = (warp - 4) >> 2;          // query tile owned by this warpgroup
     const int wq = warp & 3;                // TMEM lane quarter
     const int row = wq * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(wq * 32) << 16;
-    const bool leader = (warp == 4 && lane == 0);
-    constexpr uint32_t kSoftBar = 1;        // named barrier of the 256 softmax threads
-    constexpr uint32_t kPairBar = 2;        // +wq: named barrier of the two warps sharing a row quarter
-    uint32_t sphase[2] = {0, 0}, ophase[2] = {0, 0};
-    const int last_valid = p.n_ctx - (p.kv_tiles - 1) * kTile;                       // valid keys in the last KV tile
-    const int last_valid_h = min(max(last_valid - 64 * half, 0), 64);              // ... within this thread's half
+    const uint32_t s_addr = tmem_base + lane_base + kColS + t * kTile;
+    const uint32_t p_addr = tmem_base + lane_base + kColP + t * 64;
+    const uint32_t o_addr = tmem_base + lane_base + kColO + t * kHeadDim;
+    const bool leader = (wq == 0 && lane == 0);
+    constexpr uint32_t kTokBar = 2;         // +t: warpgroup t may start its exp sweep (the other one has finished its own)
+    constexpr uint32_t kEpiBar = 4;         // +t: warpgroup-local barrier of the output staging
+    uint32_t sphase = 0, ophase = 0;
+    const int last_valid = p.n_ctx - (p.kv_tiles - 1) * kTile;  // valid keys in the last KV tile
     const bool last_masked = last_valid < kTile;
+    if (t == 1) asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + 0), "r"(256) : "memory");  // warpgroup 0 sweeps first
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, h, q0;
       item_coords(item, b, h, q0);
-      float m_used[2] = {0.f, 0.f};  // base of the exponentials (log2 domain); lags the true row max by <= 2^32
-      float l[2] = {0.f, 0.f};       // this half's row sum
+      float m_used = 0.f;  // base of the exponentials (log2 domain); lags the true row max by <= 2^32
+      float l = 0.f;
       for (int j = 0; j < p.kv_tiles; ++j) {
         const bool masked = last_masked && (j == p.kv_tiles - 1);
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          const uint32_t s_addr = tmem_base + lane_base + kColS + t * kTile + half * 64;
-          const uint32_t p_addr = tmem_base + lane_base + kColP + t * 64 + half * 32;
-          const uint32_t o_addr = tmem_base + lane_base + kColO + t * kHeadDim + half * 32;
-          // S_t(j) complete; being issued after PV_t(j-1) it also means P_t is consumed and O_t is quiescent
-          mbar_wait(smem_u32(&s.s_full[t]), sphase[t]);
-          sphase[t] ^= 1;
+        mbar_wait(smem_u32(&s.s_full[t]), sphase);
+        sphase ^= 1;
+        tc_fence_after();
+        uint32_t v0[32], v1[32], v2[32], v3[32];
+        tmem_ld_32x32(s_addr, v0);
+        tmem_ld_32x32(s_addr + 32, v1);
+        tmem_ld_32x32(s_addr + 64, v2);
+        tmem_ld_32x32(s_addr + 96, v3);
+        tmem_wait_ld();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.s_free[t]));  // S_t is in registers: the next S_t may be produced now
+        const float mx = masked ? fmaxf(fmaxf(chunk_max<true>(v0, 0, last_valid), chunk_max<true>(v1, 32, last_valid)),
+                                        fmaxf(chunk_max<true>(v2, 64, last_valid), chunk_max<true>(v3, 96, last_valid)))
+                                : fmaxf(fmaxf(chunk_max<false>(v0, 0, kTile), chunk_max<false>(v1, 32, kTile)),
+                                        fmaxf(chunk_max<false>(v2, 64, kTile), chunk_max<false>(v3, 96, kTile)));
+        const float m_tile = mx * kLog2e;
+        if (j > 0) {  // PV_t(j-1) (issued a sweep ago) has consumed P_t and finished accumulating into O_t
+          mbar_wait(smem_u32(&s.o_done[t]), ophase);
+          ophase ^= 1;
           tc_fence_after();
-          uint32_t v0[32], v1[32];
-          tmem_ld_32x32(s_addr, v0);
-          tmem_ld_32x32(s_addr + 32, v1);
-          tmem_wait_ld();
-          // this tile's exact row max: own 64 columns from registers now, the other 64 from the partner thread later
-          const float own = masked ? fmaxf(chunk_max<true>(v0, 0, last_valid_h), chunk_max<true>(v1, 32, last_valid_h))
-                                   : fmaxf(chunk_max<false>(v0, 0, 64), chunk_max<false>(v1, 32, 64));
-          s.xmax[t][half][row] = own;
-          uint32_t pk0[16], pk1[16];
-          float lsum = 0.f;
-          if (j > 0) {  // speculate on the current base: the exponentials do not wait for the exchanged max
-            lsum = masked ? chunk_exp<true>(v0, 0, last_valid_h, m_used[t], pk0) + chunk_exp<true>(v1, 32, last_valid_h, m_used[t], pk1)
-                          : chunk_exp<false>(v0, 0, 64, m_used[t], pk0) + chunk_exp<false>(v1, 32, 64, m_used[t], pk1);
-          }
-          bar_sync(kPairBar + wq, 64);
-          const float m_tile = fmaxf(own, s.xmax[t][half ^ 1][row]) * kLog2e;
-          // first tile, or (rare) the max outgrew the base by > 2^32: move the base and redo the exponentials from the
-          // registers.  Both half-row warps see the same maxima, so they branch together.
-          const bool redo = (j == 0) || __any_sync(0xffffffffu, (m_tile - m_used[t]) > kRescaleThreshold);
-          if (redo) {
-            const float m_new = (j == 0) ? m_tile : fmaxf(m_used[t], m_tile);
-            if (j > 0) {
-              const float factor = ex2(m_used[t] - m_new);
-              l[t] *= factor;
-              uint32_t o[32];
-              tmem_ld_32x32(o_addr, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-              tmem_st_32x32(o_addr, o);
-            }
-            m_used[t] = m_new;
-            lsum = masked ? chunk_exp<true>(v0, 0, last_valid_h, m_new, pk0) + chunk_exp<true>(v1, 32, last_valid_h, m_new, pk1)
-                          : chunk_exp<false>(v0, 0, 64, m_new, pk0) + chunk_exp<false>(v1, 32, 64, m_new, pk1);
-          }
-          l[t] += lsum;
-          tmem_st_32x16(p_addr, pk0);
-          tmem_st_32x16(p_addr + 16, pk1);
-          tmem_wait_st();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&s.p_ready[t]));
         }
-      }
-      // ---- epilogue: O / l -> bf16 -> swizzled smem -> TMA store (both tiles)
+        if (j == 0) {
+          m_used = m_tile;
+        } else if (__any_sync(0xffffffffu, (m_tile - m_used) > kRescaleThreshold)) {  // rare
+          const float m_new = fmaxf(m_used, m_tile);
+          const float factor = ex2(m_used - m_new);
+          m_used = m_new;
+          l *= factor;
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(o_addr + c * 32, o);
+            tmem_wait_ld();
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        mbar_wait(smem_u32(&s.o_done[t]), ophase[t]);
-        ophase[t] ^= 1;
-        s.xsum[t][half][row] = l[t];
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+            tmem_st_32x32(o_addr + c * 32, o);
+          }
+        }
+        // ---- exp sweep.  The first kPreTokenChunks quarter(s) run beside the other warpgroup's sweep (one warp per
+        // scheduler cannot quite saturate the 16-op/clk exp pipe); the rest is exclusive (token), so the pipe never
+        // idles while this warpgroup waits for / reads its next S tile.
+        uint32_t pk[16];
+        float lsum = 0.f;
+        auto sweep_chunk = [&](const uint32_t (&v)[32], int c) {
+          lsum += masked ? chunk_exp<true>(v, 32 * c, last_valid, m_used, pk) : chunk_exp<false>(v, 32 * c, kTile, m_used, pk);
+          tmem_st_32x16(p_addr + 16 * c, pk);
+        };
+        if (kPreTokenChunks >= 1) sweep_chunk(v0, 0);
+        if (kPreTokenChunks >= 2) sweep_chunk(v1, 1);
+        asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory");
+        if (kPreTokenChunks < 1) sweep_chunk(v0, 0);
+        if (kPreTokenChunks < 2) sweep_chunk(v1, 1);
+        sweep_chunk(v2, 2);
+        sweep_chunk(v3, 3);
+        asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(256) : "memory");
+        l += lsum;
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&s.p_ready[t]));
       }
+      // ---- epilogue: O / l -> bf16 -> swizzled smem -> TMA store
+      mbar_wait(smem_u32(&s.o_done[t]), ophase);
+      ophase ^= 1;
       tc_fence_after();
-      if (leader) tma_store_wait_read<0>();  // staging tiles of the previous item have been read out
-      bar_sync(kSoftBar, 256);
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t o_addr = tmem_base + lane_base + kColO + t * kHeadDim + half * 32;
-        const float inv = 1.0f / (l[t] + s.xsum[t][half ^ 1][row]);
-        const uint32_t o_row = smem_u32(&s.o[t][0]) + row * 128;
+      if (leader) tma_store_wait_read<0>();  // staging tile of the previous item has been read out
+      bar_sync(kEpiBar + t, 128);
+      const float inv = 1.0f / l;
+      const uint32_t o_row = smem_u32(&s.o[t][0]) + row * 128;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld_32x32(o_addr, v);
+        tmem_ld_32x32(o_addr + c * 32, v);
         tmem_wait_ld();
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const int chunk = half * 4 + q;  // 16-byte chunk = 8 channels
+          const int chunk = c * 4 + q;  // 16-byte chunk = 8 channels
           const uint32_t a0 = pack_bf16x2(__uint_as_float(v[8 * q + 0]) * inv, __uint_as_float(v[8 * q + 1]) * inv);
           const uint32_t a1 = pack_bf16x2(__uint_as_float(v[8 * q + 2]) * inv, __uint_as_float(v[8 * q + 3]) * inv);
           const uint32_t a2 = pack_bf16x2(__uint_as_float(v[8 * q + 4]) * inv, __uint_as_float(v[8 * q + 5]) * inv);
@@ -341,13 +381,13 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      bar_sync(kSoftBar, 256);
+      bar_sync(kEpiBar + t, 128);
       if (leader) {
-        tma_store_3d(&p.tm_out, smem_u32(&s.o[0][0]), h * kHeadDim, q0, b);
-        tma_store_3d(&p.tm_out, smem_u32(&s.o[1][0]), h * kHeadDim, q0 + kTile, b);
+        tma_store_3d(&p.tm_out, smem_u32(&s.o[t][0]), h * kHeadDim, q0 + t * kTile, b);
         tma_store_commit();
       }
     }
+    if (t == 0) asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + 0), "r"(256) : "memory");  // absorb the last token
     if (leader) tma_store_wait<0>();
   }
 

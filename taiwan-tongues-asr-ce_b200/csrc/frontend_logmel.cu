@@ -29,6 +29,8 @@ constexpr int kThreads = kRadix * kGroups;     // 320
 constexpr int kSpan = kHop * (kTileFrames - 1) + kNfft;  // 5360 samples per tile
 constexpr int kTStride = 500;                  // per-group stride of the transpose buffer (== 20 mod 32)
 constexpr int kTRow = 25;                      // k1 stride inside a group (== 1 mod 8, >= 20)
+constexpr int kPwPitch = 33;                   // power spectra [bin][frame], odd pitch
+static_assert(kNfreq * kPwPitch <= kGroups * kTStride, "power spectra must fit in the transpose buffer");
 constexpr float kMelFloor = 1e-10f;
 constexpr float kLog10Floor = -10.0f;
 
@@ -205,10 +207,12 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         }
       }
       __syncthreads();
-      // ---------------- Hermitian split + power: frame a = 2 grp (kept in tr), frame b = 2 grp + 1 (in ti)
+      // ---------------- Hermitian split + power: frame a = 2 grp, frame b = 2 grp + 1.  The spectra are written
+      // bin-major, pw[k][frame] with a row pitch of 33 floats, so that in the mel pass lanes = frames read
+      // consecutive words (no bank conflicts) and the per-filter weight is a broadcast.
       {
-        float* zr = &s.tr[grp * kTStride];
-        float* zi = &s.ti[grp * kTStride];
+        const float* zr = &s.tr[grp * kTStride];
+        const float* zi = &s.ti[grp * kTStride];
         float pa[11], pb[11];
 #pragma unroll
         for (int i = 0; i < 11; ++i) {
@@ -220,29 +224,35 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
             split_power(zr[k], zi[k], zr[kk], zi[kk], pa[i], pb[i]);
           }
         }
-        __syncthreads();  // all Z reads done; overwrite with the power spectra
+        __syncthreads();  // all Z reads done; the (re) buffer now holds the power spectra
+        float* pw = &s.tr[2 * grp];
 #pragma unroll
         for (int i = 0; i < 11; ++i) {
           const int k = sub + kRadix * i;
           if (k < kNfreq) {
-            zr[k] = pa[i];
-            zi[k] = pb[i];
+            pw[k * kPwPitch] = pa[i];
+            pw[k * kPwPitch + 1] = pb[i];
           }
         }
       }
       __syncthreads();
-      // ---------------- mel gather + log10 + store (lanes walk time -> 128 B coalesced rows)
-      for (int idx = tid; idx < kTileFrames * n_mels; idx += kThreads) {
-        const int f = idx % kTileFrames, m = idx / kTileFrames;
-        const float* p = ((f & 1) ? s.ti : s.tr) + (f >> 1) * kTStride + s.mel_lo[m];
-        const float* w = &s.melw[s.mel_off[m]];
-        const int cnt = s.mel_cnt[m];
-        float acc = 0.f;
-        for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], p[j], acc);
-        const float v = log10f(fmaxf(acc, kMelFloor));
-        if (t0 + f < n_frames) {
-          raw[(static_cast<long long>(b) * n_mels + m) * n_frames + t0 + f] = v;
-          tmax = fmaxf(tmax, v);
+      // ---------------- mel gather + log10 + store: warp w owns filters w, w + 10, ...; lane = frame within the tile
+      {
+        const int lane = tid & 31;
+        const bool live = (t0 + lane) < n_frames;
+        float* out_col = raw + static_cast<long long>(b) * n_mels * n_frames + t0 + lane;
+        for (int m = tid >> 5; m < n_mels; m += kThreads / 32) {
+          const float* pwm = &s.tr[s.mel_lo[m] * kPwPitch + lane];
+          const float* w = &s.melw[s.mel_off[m]];
+          const int cnt = s.mel_cnt[m];
+          float acc = 0.f;
+          for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], pwm[j * kPwPitch], acc);
+          // log10 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate); the floor is returned exactly
+          const float v = acc > kMelFloor ? __log2f(acc) * 0.30102999566398120f : kLog10Floor;
+          if (live) {
+            out_col[static_cast<long long>(m) * n_frames] = v;
+            tmax = fmaxf(tmax, v);
+          }
         }
       }
       __syncthreads();  // power spectra consumed before the next tile's pass 1 overwrites the buffer

@@ -6,7 +6,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libttasr_b200.so")
+# TTASR_LIB_PATH selects an experiment build of the same ABI (tools/, profiling); the default is the in-tree library
+_LIB_PATH = os.environ.get("TTASR_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libttasr_b200.so")
 
 TTASR_OK = 0
 PCM_F32, PCM_I16 = 0, 1
