@@ -354,10 +354,19 @@ def run_ours(args):
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
 
-    # ---- end-to-end arm (host buffers in, host buffers out)
+    # ---- end-to-end arm (host buffers in, host buffers out) through the public pipeline object: every step's PCM
+    # is copied from pinned host memory and every step's hidden states are copied back, inside the timed region;
+    # stream_host overlaps step k's kernels with the copy-in of step k+1 and the copy-out of step k-1.
+    pipe = ttasr.B200LogMelEncoder(fe, enc)
     for _ in range(min(args.warmup, 3)):
         step_host()
-    e2e_ms, _ = timed(step_host, args.steps)
+    pipe.stream_host([host_pcm] * 2, [host_out] * 2)
+    torch.cuda.synchronize()
+
+    def run_stream():
+        pipe.stream_host([host_pcm] * args.steps, [host_out] * args.steps)
+
+    e2e_ms, _ = timed(run_stream, 1)
     e2e_value = n_gpus * B * CHUNK_SECONDS * args.steps / (e2e_ms / 1e3)
 
     if rank != 0:

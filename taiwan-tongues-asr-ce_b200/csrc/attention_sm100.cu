@@ -29,11 +29,14 @@ constexpr int kTileBytes = kTile * kHeadDim * 2;  // 16 KB
 constexpr int kKvStages = 4;
 constexpr int kAttnThreads = 384;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr bool kEmulateQuarter = false;  // every 4th exponential on the FMA pipe instead of MUFU: measured slower (0.79 vs 0.73 ms)
 #ifndef TTASR_ATTN_PRETOKEN
 #define TTASR_ATTN_PRETOKEN 1
 #endif
+#ifndef TTASR_ATTN_EMUL
+#define TTASR_ATTN_EMUL 0
+#endif
 constexpr int kPreTokenChunks = TTASR_ATTN_PRETOKEN;  // quarters of the exp sweep done outside the token
+constexpr bool kPreTokenEmulate = TTASR_ATTN_EMUL != 0;  // ... on the FMA pipe instead of MUFU
 constexpr float kRescaleThreshold = 32.0f;  // log2 units: P stays <= 2^32 (bf16 range 2^127, O and l are fp32)
 
 // TMEM column map
@@ -95,7 +98,7 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int col0, in
 }
 
 // p_i = 2^(s_i*log2e - m_used) for 32 columns -> 16 packed bf16 pairs; returns the fp32 sum
-template <bool MASKED>
+template <bool MASKED, bool EMUL>
 __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], int col0, int valid, float m_used, uint32_t (&pk)[16]) {
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
@@ -105,8 +108,8 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], int col0, in
       if (col0 + 2 * i >= valid) x0 = -INFINITY;
       if (col0 + 2 * i + 1 >= valid) x1 = -INFINITY;
     }
-    const float p0 = ex2(fmaf(x0, kLog2e, -m_used));
-    const float p1 = ((i & 1) && kEmulateQuarter) ? ex2_fma(fmaf(x1, kLog2e, -m_used)) : ex2(fmaf(x1, kLog2e, -m_used));
+    const float p0 = EMUL ? ex2_fma(fmaf(x0, kLog2e, -m_used)) : ex2(fmaf(x0, kLog2e, -m_used));
+    const float p1 = EMUL ? ex2_fma(fmaf(x1, kLog2e, -m_used)) : ex2(fmaf(x1, kLog2e, -m_used));
     sum0 += p0;
     sum1 += p1;
     pk[i] = pack_bf16x2(p0, p1);
@@ -337,11 +340,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         uint32_t pk[16];
         float lsum = 0.f;
         auto sweep_chunk = [&](const uint32_t (&v)[32], int c) {
-          lsum += masked ? chunk_exp<true>(v, 32 * c, last_valid, m_used, pk) : chunk_exp<false>(v, 32 * c, kTile, m_used, pk);
+          lsum += masked ? chunk_exp<true, false>(v, 32 * c, last_valid, m_used, pk)
+                         : chunk_exp<false, false>(v, 32 * c, kTile, m_used, pk);
           tmem_st_32x16(p_addr + 16 * c, pk);
         };
-        if (kPreTokenChunks >= 1) sweep_chunk(v0, 0);
-        if (kPreTokenChunks >= 2) sweep_chunk(v1, 1);
+        // outside the token the exponentials go through the FMA/ALU pipes (ex2_fma), which the sweeping warpgroup
+        // leaves idle, instead of competing with it for the exp pipe
+        auto sweep_chunk_fma = [&](const uint32_t (&v)[32], int c) {
+          lsum += masked ? chunk_exp<true, kPreTokenEmulate>(v, 32 * c, last_valid, m_used, pk)
+                         : chunk_exp<false, kPreTokenEmulate>(v, 32 * c, kTile, m_used, pk);
+          tmem_st_32x16(p_addr + 16 * c, pk);
+        };
+        if (kPreTokenChunks >= 1) sweep_chunk_fma(v0, 0);
+        if (kPreTokenChunks >= 2) sweep_chunk_fma(v1, 1);
         asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory");
         if (kPreTokenChunks < 1) sweep_chunk(v0, 0);
         if (kPreTokenChunks < 2) sweep_chunk(v1, 1);

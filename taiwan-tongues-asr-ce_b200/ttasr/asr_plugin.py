@@ -1,0 +1,160 @@
+"""`B200ASR`: the reference's streaming ASR plugin (`ASRInterface`, REF api/stt_streaming/src/asr/asr_interface.py:1-15)
+on the B200 hot path, selectable from `ASRFactory.create_asr_pipeline("b200", ...)` (asr_factory.py:9-30).
+
+What changes against `FasterWhisperASR.transcribe` (faster_whisper_asr.py:151-267):
+  * the int16 PCM of `client.scratch_buffer` goes to the GPU as is (no temp WAV round trip, audio_utils.py:5-29);
+    right-padding to 30 s is virtual (`n_valid`), the kernel never reads the padding;
+  * utterances of all connected clients that are ready within `batch_window_s` are run as ONE front-end + encoder
+    launch instead of blocking the event loop once per client;
+  * log-mel + encoder run in libttasr_b200.so; decoding stays with the host application through `decode_fn`
+    (HF `generate(encoder_outputs=...)`, a CTranslate2 decoder, ...), which receives the hidden states on the GPU.
+
+The result dictionary has the reference's fields (faster_whisper_asr.py:240-255).
+"""
+from __future__ import annotations
+
+import asyncio
+import time
+from dataclasses import dataclass, field
+from typing import Any, Callable
+
+from . import _lib
+from .pipeline import B200LogMelEncoder
+
+
+@dataclass
+class Utterance:
+    """One client's scratch buffer on its way through the batcher."""
+    pcm_i16: Any                      # torch.int16 CPU tensor [n]
+    client: Any
+    future: Any = None
+    meta: dict = field(default_factory=dict)
+
+
+def pcm_bytes_to_tensor(buf, samples_width: int = 2):
+    """bytes / bytearray of little-endian int16 mono PCM (the WebSocket wire format, streaming_asr.py:223-226)."""
+    import numpy as np
+    import torch
+
+    if samples_width != 2:
+        raise ValueError(f"only 16-bit PCM is supported (samples_width={samples_width})")
+    n = len(buf) // 2
+    return torch.from_numpy(np.frombuffer(bytes(buf[: 2 * n]), dtype="<i2").copy())
+
+
+class MicroBatcher:
+    """Collects utterances for at most `window_s` (or until `max_batch`) and encodes them in one launch."""
+
+    def __init__(self, pipeline: B200LogMelEncoder, window_s: float = 0.005, max_batch: int = 64):
+        self.pipeline = pipeline
+        self.window_s = window_s
+        self.max_batch = max_batch
+        self.n_samples = pipeline.feature_extractor.n_samples
+        self._pending: list[Utterance] = []
+        self._flusher = None
+        self.launches = 0
+        self.encoded = 0
+
+    def encode_batch(self, utterances: list[Utterance]):
+        """Synchronous core: ragged int16 rows -> hidden states [B, 1500, d] (CUDA)."""
+        import torch
+
+        B = len(utterances)
+        lens = [min(int(u.pcm_i16.numel()), self.n_samples) for u in utterances]
+        width = max(max(lens), 1)
+        width = (width + 7) // 8 * 8  # 16-byte rows keep the bulk-copy path
+        host = torch.zeros((B, width), dtype=torch.int16).pin_memory()
+        for i, u in enumerate(utterances):
+            host[i, : lens[i]] = u.pcm_i16[: lens[i]]
+        dev = self.pipeline.device
+        pcm = host.to(dev, non_blocking=True)
+        n_valid = torch.tensor(lens, dtype=torch.int32).to(dev, non_blocking=True)
+        hidden = self.pipeline.encode_device(pcm, n_valid=n_valid)
+        self.launches += 1
+        self.encoded += B
+        return hidden, lens
+
+    async def submit(self, utt: Utterance):
+        loop = asyncio.get_running_loop()
+        utt.future = loop.create_future()
+        self._pending.append(utt)
+        if len(self._pending) >= self.max_batch:
+            self._flush()
+        elif self._flusher is None:
+            self._flusher = loop.call_later(self.window_s, self._flush)
+        return await utt.future
+
+    def _flush(self):
+        if self._flusher is not None:
+            self._flusher.cancel()
+            self._flusher = None
+        batch, self._pending = self._pending[: self.max_batch], self._pending[self.max_batch:]
+        if not batch:
+            return
+        try:
+            hidden, lens = self.encode_batch(batch)
+            for i, u in enumerate(batch):
+                if not u.future.done():
+                    u.future.set_result((hidden[i: i + 1], lens[i]))
+        except Exception as e:  # surfaced to every waiter; the reference's wrappers log and return None
+            for u in batch:
+                if not u.future.done():
+                    u.future.set_exception(e)
+        if self._pending:
+            self._flusher = asyncio.get_running_loop().call_later(self.window_s, self._flush)
+
+
+class B200ASR:
+    """ASRInterface implementation (duck-typed: `async transcribe(client)`, `warm_up()`)."""
+
+    def __init__(self, pipeline: B200LogMelEncoder, decode_fn: Callable[[Any, dict], dict],
+                 batch_window_s: float = 0.005, max_batch: int = 64, language: str = "zh", **kwargs):
+        """decode_fn(hidden [1, 1500, d] CUDA bf16, info dict) -> {"text": str, "words": [...], "language": ...,
+        "language_probability": ...}; it owns beam search and text post-processing exactly as the reference's
+        decoder does today."""
+        self.pipeline = pipeline
+        self.decode_fn = decode_fn
+        self.batcher = MicroBatcher(pipeline, batch_window_s, max_batch)
+        self.language = language
+        self.device = "cuda"
+        self.compute_type = "bfloat16"
+        self.model_size = kwargs.get("model_size")
+
+    async def transcribe(self, client):
+        try:
+            pcm = pcm_bytes_to_tensor(client.scratch_buffer, getattr(client, "samples_width", 2))
+            if pcm.numel() == 0:
+                return None
+            hidden, n = await self.batcher.submit(Utterance(pcm, client))
+            info = {"language": self.language, "n_samples": n,
+                    "sampling_rate": self.pipeline.feature_extractor.sampling_rate}
+            out = self.decode_fn(hidden, info) or {}
+            text = out.get("text")
+            if not text:
+                return None
+            t0 = getattr(client, "last_start_time", 0) or 0
+            words = out.get("words") or []
+            duration = words[-1]["end"] if words else n / info["sampling_rate"]
+            return {
+                "language": out.get("language", self.language),
+                "language_probability": out.get("language_probability"),
+                "final": True,
+                "text": text,
+                "duration": duration,
+                "words": [{"word": w.get("word", ""), "start": (w.get("start", 0) or 0) + t0,
+                           "end": (w.get("end", 0) or 0) + t0, "probability": w.get("probability")} for w in words],
+            }
+        except _lib.TtasrError:
+            raise  # no silent CPU fallback: a missing GPU / library is a deployment error
+        except Exception:
+            return None  # same contract as the reference wrapper (faster_whisper_asr.py:260-267)
+
+    def warm_up(self):
+        """One 1 s utterance through the kernels (module load, TMA descriptor caches, allocator)."""
+        import torch
+
+        t0 = time.time()
+        utt = Utterance(torch.zeros(16000, dtype=torch.int16), None)
+        hidden, _ = self.batcher.encode_batch([utt])
+        torch.cuda.synchronize(self.pipeline.device)
+        return {"warm_up_seconds": time.time() - t0, "hidden_shape": tuple(hidden.shape)}

@@ -48,3 +48,51 @@ class B200LogMelEncoder:
             out_host.copy_(hidden, non_blocking=True)
             return out_host
         return hidden
+
+    def stream_host(self, batches, outs):
+        """Pipelined host-to-host run over a sequence of batches: while batch k is in the kernels, batch k+1's PCM is
+        copied in and batch k-1's hidden states are copied out (three streams, double-buffered device staging).
+
+        batches: sequence of pinned CPU tensors [B, n_samples] (float32 or int16, same shape/dtype);
+        outs:    sequence of pinned CPU tensors [B, 1500, d] bf16 receiving the hidden states.
+        Returns when everything has been enqueued; synchronise the current stream (or the device) to wait."""
+        import torch
+
+        batches, outs = list(batches), list(outs)
+        if len(batches) != len(outs):
+            raise _lib.TtasrError(-2, "stream_host needs one output buffer per batch")
+        if not batches:
+            return
+        main = torch.cuda.current_stream(self.device)
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        h2d, d2h = self._copy_streams
+        shape, dtype = tuple(batches[0].shape), batches[0].dtype
+        if getattr(self, "_ring", None) is None or self._ring[0].shape != shape or self._ring[0].dtype != dtype:
+            self._ring = [torch.empty(shape, dtype=dtype, device=self.device) for _ in range(2)]
+        in_ready = [torch.cuda.Event() for _ in batches]
+        in_free = [torch.cuda.Event() for _ in batches]
+        out_ready = [torch.cuda.Event() for _ in batches]
+        hidden = [None, None]
+        h2d.wait_stream(main)
+        d2h.wait_stream(main)
+        for k, pcm in enumerate(batches):
+            buf = self._ring[k & 1]
+            with torch.cuda.stream(h2d):
+                if k >= 2:
+                    h2d.wait_event(in_free[k - 2])  # the front end has consumed this staging buffer
+                buf.copy_(pcm, non_blocking=True)
+                in_ready[k].record(h2d)
+            main.wait_event(in_ready[k])
+            if k >= 2:
+                main.wait_event(out_ready[k - 2])  # hidden[k & 1] has been copied out before it is overwritten
+            _, tm = self.feature_extractor.extract(buf, return_time_major=True)
+            in_free[k].record(main)
+            hidden[k & 1] = self.encoder.encode(tm, time_major_ld=tm.shape[2])
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(d2h):
+                d2h.wait_event(done)
+                outs[k].copy_(hidden[k & 1], non_blocking=True)
+                out_ready[k].record(d2h)
+        main.wait_stream(d2h)

@@ -100,3 +100,80 @@ def test_encoder_small_config2_sample(cuda_device, arch_name):
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
     got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
     _check(got, ref)
+
+
+def test_pipelined_host_stream_matches_single_calls(cuda_device):
+    """stream_host overlaps copy-in / kernels / copy-out over a batch sequence; results equal the unpipelined path."""
+    import torch
+    from ttasr import B200LogMelEncoder, B200WhisperFeatureExtractor
+
+    arch, w, enc = _build("micro")
+    pipe = B200LogMelEncoder(B200WhisperFeatureExtractor(feature_size=arch.n_mels), enc)
+    batches = [torch.from_numpy(np.stack([OF.pad_or_trim(OF.synth_noise(20 + 2 * k)),
+                                          OF.pad_or_trim(OF.synth_tones(21 + 2 * k))])).pin_memory() for k in range(5)]
+    outs = [torch.empty((2, 1500, arch.d_model), dtype=torch.bfloat16).pin_memory() for _ in batches]
+    pipe.stream_host(batches, outs)
+    torch.cuda.synchronize()
+    for b, o in zip(batches, outs):
+        ref = pipe.encode_device(b.to(cuda_device)).cpu()
+        assert torch.equal(o, ref)
+
+
+def test_streaming_plugin_end_to_end(cuda_device):
+    """B200ASR (the reference's ASRInterface): int16 scratch buffers of several clients -> one batched launch ->
+    hidden states identical to encoding each utterance alone; decode stays with the host callback."""
+    import asyncio
+    import types
+    import torch
+    from ttasr import B200LogMelEncoder, B200WhisperFeatureExtractor
+    from ttasr.asr_plugin import B200ASR
+
+    arch, w, enc = _build("micro")
+    pipe = B200LogMelEncoder(B200WhisperFeatureExtractor(feature_size=arch.n_mels), enc)
+    seen = {}
+
+    def decode(hidden, info):
+        seen[info["n_samples"]] = hidden.float().cpu()
+        return {"text": "測試", "words": []}
+
+    asr = B200ASR(pipe, decode, batch_window_s=0.02)
+    assert asr.warm_up()["hidden_shape"] == (1, 1500, arch.d_model)
+    rng = np.random.default_rng(8)
+    pcm = [(rng.standard_normal(n) * 2000).astype("<i2") for n in (16000, 52345, 80000)]
+    clients = [types.SimpleNamespace(scratch_buffer=bytearray(p.tobytes()), samples_width=2, last_start_time=0.0,
+                                     client_id=i) for i, p in enumerate(pcm)]
+
+    async def run():
+        return await asyncio.gather(*(asr.transcribe(c) for c in clients))
+
+    launches0 = asr.batcher.launches
+    results = asyncio.run(run())
+    assert all(r and r["text"] == "測試" and r["final"] for r in results)
+    assert asr.batcher.launches == launches0 + 1  # three clients, one launch
+    for p in pcm:
+        feats = OF.log_mel(p.astype(np.float32) / 32768.0, arch.n_mels)[None]
+        ref = OE.encoder_forward(torch.from_numpy(feats), w, arch)
+        _check(seen[len(p)].numpy(), ref.numpy())
+
+
+def test_faster_whisper_seams(cuda_device):
+    """compat_faster_whisper: whole-file log-mel with the global clamp + encode() of a padded window."""
+    import types
+    import torch
+    from ttasr import B200WhisperFeatureExtractor
+    from ttasr.compat_faster_whisper import patch_model
+
+    arch, w, enc = _build("micro")
+    model = patch_model(types.SimpleNamespace(), enc, B200WhisperFeatureExtractor(feature_size=arch.n_mels))
+    rng = np.random.default_rng(4)
+    wave = (0.1 * rng.standard_normal(16000 * 41 + 77)).astype(np.float32)
+    feats = model.feature_extractor(wave, padding=160)
+    padded = np.concatenate([wave, np.zeros(160, np.float32)])
+    ref = OF.log_mel_unclamped(padded, arch.n_mels)[:, :-1]
+    ref = (np.maximum(ref, ref.max() - 8.0) + 4.0) / 4.0
+    assert feats.shape == ref.shape and np.abs(feats - ref).max() <= 1e-4
+    window = feats[:, 3000:]  # second 30 s window is short: encode() pads it in feature space like faster-whisper
+    hidden = model.encode(window)
+    padded_window = np.concatenate([window, np.zeros((arch.n_mels, 3000 - window.shape[1]), np.float32)], axis=1)
+    ref_h = OE.encoder_forward(torch.from_numpy(padded_window[None]), w, arch)
+    _check(hidden.float().cpu().numpy(), ref_h.numpy())

@@ -123,3 +123,62 @@ def test_fft400_factorisation_on_the_host(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
     assert float(r.stdout.split()[1]) < 2e-3
+
+
+def test_file_level_features_match_whole_file_stft(monkeypatch):
+    """faster-whisper semantics (whole-file log-mel, global clamp) assembled from 30 s chunk calls: the chunking /
+    halo / re-clamp logic of ttasr.compat_faster_whisper, with the CUDA extractor replaced by the oracle."""
+    import torch
+    from ttasr import B200WhisperFeatureExtractor
+    from ttasr.compat_faster_whisper import FileFeatureExtractor
+
+    fe = B200WhisperFeatureExtractor(feature_size=80)
+    monkeypatch.setattr(fe, "_torch_device", lambda: torch.device("cpu"))
+    monkeypatch.setattr(fe, "extract", lambda pcm, **kw: torch.from_numpy(OF.log_mel_batch(pcm.numpy(), 80)))
+    rng = np.random.default_rng(3)
+    wave = (0.05 * rng.standard_normal(16000 * 75 + 1234)).astype(np.float32)  # 75 s -> 3 chunks
+    wave[16000 * 40:] *= 20.0                                                   # the file max sits in a later chunk
+    got = FileFeatureExtractor(fe)(wave, padding=160)
+    padded = np.concatenate([wave, np.zeros(160, np.float32)])
+    ref = OF.log_mel_unclamped(padded, 80)[:, :-1]
+    ref = (np.maximum(ref, ref.max() - 8.0) + 4.0) / 4.0
+    assert got.shape == ref.shape == (80, padded.shape[0] // 160)
+    assert np.abs(got - ref).max() < 2e-6
+
+
+def test_asr_plugin_microbatcher_batches_concurrent_clients():
+    """B200ASR (ASRInterface): three clients ready within one window -> ONE encode launch; reference result fields."""
+    import asyncio
+    import types
+    import torch
+    from ttasr.asr_plugin import B200ASR, pcm_bytes_to_tensor
+
+    calls = []
+
+    class FakePipe:  # stands in for the CUDA pipeline: records what would be launched
+        device = torch.device("cpu")
+        feature_extractor = types.SimpleNamespace(n_samples=480000, sampling_rate=16000)
+
+        def encode_device(self, pcm, n_valid=None):
+            calls.append((tuple(pcm.shape), n_valid.tolist()))
+            return torch.zeros((pcm.shape[0], 1500, 8))
+
+    monkey_pin = torch.Tensor.pin_memory
+    torch.Tensor.pin_memory = lambda self, *a, **k: self  # no CUDA on the CPU box
+    try:
+        asr = B200ASR(FakePipe(), lambda hidden, info: {"text": f"n={info['n_samples']}", "words": []},
+                      batch_window_s=0.01)
+        clients = [types.SimpleNamespace(scratch_buffer=bytearray(np.full(n, 7, "<i2").tobytes()), samples_width=2,
+                                         last_start_time=1.5, client_id=i) for i, n in enumerate((16000, 40000, 24001))]
+
+        async def run():
+            return await asyncio.gather(*(asr.transcribe(c) for c in clients))
+
+        results = asyncio.run(run())
+    finally:
+        torch.Tensor.pin_memory = monkey_pin
+    assert len(calls) == 1 and calls[0][0][0] == 3 and calls[0][1] == [16000, 40000, 24001]
+    assert [r["text"] for r in results] == ["n=16000", "n=40000", "n=24001"]
+    assert all(r["final"] and r["language"] == "zh" and set(r) == {"language", "language_probability", "final",
+                                                                    "text", "duration", "words"} for r in results)
+    assert pcm_bytes_to_tensor(bytearray(b"\x01\x00\xff\xff\x05")).tolist() == [1, -1]
