@@ -101,6 +101,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
     b = static_cast<int>(tile / tiles_per_chunk);
     tt = static_cast<int>(tile % tiles_per_chunk);
     valid = n_valid ? min(max(n_valid[b], 0), n_samples) : n_samples;
+    valid = static_cast<int>(min(static_cast<long long>(valid), row_stride));  // never read past the row
     const int start = tt * kTileFrames * kHop - kNfft / 2;
     if (start >= valid && valid < n_samples - kNfft) return 0;
     if (rows_aligned && start >= 0 && start + kSpan <= valid) return 1;

@@ -434,10 +434,22 @@ cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, con
     return cudaErrorInvalidValue;
   }
   if (c.addend && !c.out_f32) { *why = "gemm: addend requires fp32 output"; return cudaErrorInvalidValue; }
-  const int bn = (c.n % 256 == 0) ? 256 : 128;
+  // Tile shape: 256-wide tiles on CTA pairs when there is enough work to fill the machine (batch throughput);
+  // for latency-bound small problems (streaming: one or a few chunks) fall back to shapes that make more tiles.
+  if (c.cta_group != 0 && c.cta_group != 1 && c.cta_group != 2) { *why = "gemm: cta_group must be 0, 1 or 2"; return cudaErrorInvalidValue; }
+  int bn = (c.n % 256 == 0) ? 256 : 128;
   int cg = c.cta_group == 0 ? 2 : c.cta_group;
-  if (cg != 1 && cg != 2) { *why = "gemm: cta_group must be 0, 1 or 2"; return cudaErrorInvalidValue; }
-
+  if (c.cta_group == 0) {
+    auto tiles = [&](int bn_, int cg_) {
+      return static_cast<long long>((c.rows + kBM * cg_ - 1) / (kBM * cg_)) * c.nbatch * (c.n / bn_);
+    };
+    const int cand[3][2] = {{bn, 2}, {128, 2}, {128, 1}};
+    for (int i = 0; i < 3; ++i) {
+      bn = cand[i][0];
+      cg = cand[i][1];
+      if (tiles(bn, cg) * 10 >= static_cast<long long>(num_sms / cg) * 6) break;  // >= 0.6 wave: big tiles win above that
+    }
+  }
   GemmParams p{};
   p.bias = c.bias;
   p.mode = c.mode;

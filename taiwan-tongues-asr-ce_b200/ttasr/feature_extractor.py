@@ -123,8 +123,7 @@ class B200WhisperFeatureExtractor:
             n_valid = _lib.require_cuda_tensor(n_valid, "n_valid").to(torch.int32)
             if n_valid.numel() != B:
                 raise _lib.TtasrError(-2, "n_valid must hold one length per row")
-            if int(n_valid.max()) > stride:
-                raise _lib.TtasrError(-2, "n_valid exceeds the row length")
+            # (lengths beyond the row are clamped by the kernel; no host sync here, so the call is graph-capturable)
             nv_ptr = n_valid.data_ptr()
         elif stride < self.n_samples:
             raise _lib.TtasrError(-2, f"rows hold {stride} samples < {self.n_samples}; pass n_valid for ragged input")

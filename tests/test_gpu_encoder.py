@@ -177,3 +177,47 @@ def test_faster_whisper_seams(cuda_device):
     padded_window = np.concatenate([window, np.zeros((arch.n_mels, 3000 - window.shape[1]), np.float32)], axis=1)
     ref_h = OE.encoder_forward(torch.from_numpy(padded_window[None]), w, arch)
     _check(hidden.float().cpu().numpy(), ref_h.numpy())
+
+
+def test_large_v3_single_chunk_against_oracle(cuda_device):
+    """The headline architecture (config 3 shape: d=1280, 32 layers, 20 heads, 128 mels) on one chunk; the fp32 oracle
+    takes a few seconds on the host.  Gate as stated in DESIGN.md section 2."""
+    import torch
+
+    arch, w, enc = _build("large-v3")
+    feats = OF.log_mel(OF.synth_tones(31), arch.n_mels)[None]
+    ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
+    got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
+    s = _check(got, ref)
+    print("large-v3 parity:", s)
+
+
+def test_forward_can_be_captured_in_a_cuda_graph(cuda_device):
+    """Everything behind ttasr_frontend_run / ttasr_encoder_forward is stream-ordered with no host synchronisation,
+    so the latency-bound streaming shape (one utterance, config 5) can be replayed as a CUDA graph."""
+    import torch
+    from ttasr import B200LogMelEncoder, B200WhisperFeatureExtractor
+
+    arch, w, enc = _build("tiny")
+    pipe = B200LogMelEncoder(B200WhisperFeatureExtractor(feature_size=arch.n_mels), enc)
+    pcm = torch.from_numpy(OF.pad_or_trim(OF.synth_noise(41))[None]).to(cuda_device)
+    eager = pipe.encode_device(pcm).clone()
+    static_in = pcm.clone()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            pipe.encode_device(static_in)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        static_out = pipe.encode_device(static_in)
+    static_in.copy_(torch.from_numpy(OF.pad_or_trim(OF.synth_tones(42))[None]).to(cuda_device))
+    graph.replay()
+    torch.cuda.synchronize()
+    other = pipe.encode_device(static_in)
+    assert torch.equal(static_out, other) and not torch.equal(static_out, eager)
+    static_in.copy_(pcm)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(static_out, eager)
