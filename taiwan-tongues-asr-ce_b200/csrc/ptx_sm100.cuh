@@ -309,16 +309,17 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float e = p * t * ex2_approx(-1.4426950408889634f * z * z);  // 1 - erf(z)
-  const float half_erfc = 0.5f * e;        // Phi(-|x|)
-  const float phi = x >= 0.f ? 1.0f - half_erfc : half_erfc;
-  return x * phi;
+  // Phi(-|x|) = 0.5 * erfc(|x| / sqrt 2) = (a1 t + ... + a5 t^5) * exp(-x^2 / 2) / 2,  t = 1 / (1 + p |x| / sqrt 2)
+  // gelu(x) = x * Phi(x) = relu(x) - |x| * Phi(-|x|)   (both signs, no select)
+  const float ax = fabsf(x);
+  const float t = rcp_approx(fmaf(0.23164189f, ax, 1.0f));
+  const float e = ex2_approx((x * x) * -0.72134752044448170f);
+  float p = fmaf(0.5307027145f, t, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float h = (p * t) * e;
+  return fmaf(-ax, h, fmaxf(x, 0.0f));
 }
 
 }  // namespace ttasr
