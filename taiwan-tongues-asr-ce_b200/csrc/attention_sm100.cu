@@ -445,11 +445,10 @@ cudaError_t attention_launch(const void* qkv, void* out, int batch, int n_ctx, i
     }
   }
   const int smem = static_cast<int>(sizeof(AttnSmem)) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     cudaError_t e = cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
   attention_kernel<<<grid, kAttnThreads, smem, stream>>>(p);

@@ -317,13 +317,12 @@ cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride,
   const long long total = static_cast<long long>(batch) * tiles_per_chunk;
   if (total == 0) return cudaSuccess;
   const size_t smem = sizeof(FrontSmem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(logmel_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(logmel_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   fill_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(chunk_max, batch, -INFINITY);
   const int grid = static_cast<int>(total < 2LL * num_sms ? total : 2LL * num_sms);

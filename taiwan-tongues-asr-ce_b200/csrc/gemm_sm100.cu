@@ -364,11 +364,10 @@ template <int BN, int CG, int ACT, bool HAS_ADD, bool OUT_F32>
 cudaError_t launch_variant(const GemmParams& p, int num_sms, cudaStream_t stream) {
   using C = Cfg<BN, CG, HAS_ADD>;
   auto kern = gemm_kernel<BN, CG, ACT, HAS_ADD, OUT_F32>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_done;
+  if (attr_done.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   int clusters = num_sms / CG;
   if (clusters > p.num_tiles) clusters = p.num_tiles;

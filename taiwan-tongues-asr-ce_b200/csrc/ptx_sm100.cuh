@@ -9,6 +9,20 @@
 
 namespace ttasr {
 
+// cudaFuncSetAttribute is per device: remember which devices a kernel has been configured on (one flag set per
+// kernel instantiation; benign race: setting the attribute twice is harmless)
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 #ifndef TTASR_WAIT_TIMEOUT_CYCLES
 #define TTASR_WAIT_TIMEOUT_CYCLES (4000000000ll)  // ~2 s: a protocol bug traps instead of hanging the GPU
 #endif
