@@ -32,6 +32,9 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef TTASR_ATTN_PRETOKEN
 #define TTASR_ATTN_PRETOKEN 1
 #endif
+#ifndef TTASR_ATTN_PIPE
+#define TTASR_ATTN_PIPE 0
+#endif
 #ifndef TTASR_ATTN_EMUL
 #define TTASR_ATTN_EMUL 0
 #endif
@@ -110,6 +113,37 @@ __device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], int col0, in
     }
     const float p0 = EMUL ? ex2_fma(fmaf(x0, kLog2e, -m_used)) : ex2(fmaf(x0, kLog2e, -m_used));
     const float p1 = EMUL ? ex2_fma(fmaf(x1, kLog2e, -m_used)) : ex2(fmaf(x1, kLog2e, -m_used));
+    sum0 += p0;
+    sum1 += p1;
+    pk[i] = pack_bf16x2(p0, p1);
+  }
+  return sum0 + sum1;
+}
+
+__device__ __forceinline__ void mask_tail(uint32_t (&v)[32], int col0, int valid) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (col0 + i >= valid) v[i] = 0xff800000u;  // -inf
+}
+
+// Software-pipelined form of the sweep: the exponentials of a 32-column chunk are written back over the scores in
+// place (exp_inplace), and their row sum / bf16 packing (sum_pack) is issued one chunk later, so the FADD / F2FP
+// consumers never sit right behind the MUFU.EX2 that feeds them (ptxas schedules them 2 MUFUs behind, which stalls a
+// lone warp on the exp latency: 14.6 instead of 8 cycles per exponential).
+template <bool MASKED>
+__device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], int col0, int valid, float m_used) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    float x = __uint_as_float(v[i]);
+    if (MASKED && col0 + i >= valid) x = -INFINITY;
+    v[i] = __float_as_uint(ex2(fmaf(x, kLog2e, -m_used)));
+  }
+}
+__device__ __forceinline__ float sum_pack(const uint32_t (&v)[32], uint32_t (&pk)[16]) {
+  float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float p0 = __uint_as_float(v[2 * i]), p1 = __uint_as_float(v[2 * i + 1]);
     sum0 += p0;
     sum1 += p1;
     pk[i] = pack_bf16x2(p0, p1);
@@ -307,10 +341,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s.s_free[t]));  // S_t is in registers: the next S_t may be produced now
-        const float mx = masked ? fmaxf(fmaxf(chunk_max<true>(v0, 0, last_valid), chunk_max<true>(v1, 32, last_valid)),
-                                        fmaxf(chunk_max<true>(v2, 64, last_valid), chunk_max<true>(v3, 96, last_valid)))
-                                : fmaxf(fmaxf(chunk_max<false>(v0, 0, kTile), chunk_max<false>(v1, 32, kTile)),
-                                        fmaxf(chunk_max<false>(v2, 64, kTile), chunk_max<false>(v3, 96, kTile)));
+        if (masked) {  // last KV tile only: keys >= n_ctx become -inf once, so max and sweep stay branch-free
+          mask_tail(v0, 0, last_valid);
+          mask_tail(v1, 32, last_valid);
+          mask_tail(v2, 64, last_valid);
+          mask_tail(v3, 96, last_valid);
+        }
+        const float mx = fmaxf(fmaxf(chunk_max<false>(v0, 0, kTile), chunk_max<false>(v1, 32, kTile)),
+                               fmaxf(chunk_max<false>(v2, 64, kTile), chunk_max<false>(v3, 96, kTile)));
         const float m_tile = mx * kLog2e;
         if (j > 0) {  // PV_t(j-1) (issued a sweep ago) has consumed P_t and finished accumulating into O_t
           mbar_wait(smem_u32(&s.o_done[t]), ophase);
@@ -337,18 +375,42 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         // ---- exp sweep.  The first kPreTokenChunks quarter(s) run beside the other warpgroup's sweep (one warp per
         // scheduler cannot quite saturate the 16-op/clk exp pipe); the rest is exclusive (token), so the pipe never
         // idles while this warpgroup waits for / reads its next S tile.
+#if TTASR_ATTN_PIPE
+        uint32_t pk[16];
+        float lsum = 0.f;
+        auto stage_a = [&](uint32_t (&v)[32], int c) {
+          exp_inplace<false>(v, 32 * c, kTile, m_used);
+        };
+        auto stage_b = [&](const uint32_t (&v)[32], int c) {
+          lsum += sum_pack(v, pk);
+          tmem_st_32x16(p_addr + 16 * c, pk);
+        };
+        auto tok_acquire = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory"); };
+        if (kPreTokenChunks == 0) tok_acquire();
+        stage_a(v0, 0);
+        if (kPreTokenChunks == 1) tok_acquire();
+        stage_a(v1, 1);
+        stage_b(v0, 0);
+        if (kPreTokenChunks == 2) tok_acquire();
+        stage_a(v2, 2);
+        stage_b(v1, 1);
+        if (kPreTokenChunks == 3) tok_acquire();
+        stage_a(v3, 3);
+        if (kPreTokenChunks == 4) tok_acquire();
+        asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(256) : "memory");  // last exp issued
+        stage_b(v2, 2);
+        stage_b(v3, 3);
+#else
         uint32_t pk[16];
         float lsum = 0.f;
         auto sweep_chunk = [&](const uint32_t (&v)[32], int c) {
-          lsum += masked ? chunk_exp<true, false>(v, 32 * c, last_valid, m_used, pk)
-                         : chunk_exp<false, false>(v, 32 * c, kTile, m_used, pk);
+          lsum += chunk_exp<false, false>(v, 32 * c, kTile, m_used, pk);
           tmem_st_32x16(p_addr + 16 * c, pk);
         };
         // outside the token the exponentials go through the FMA/ALU pipes (ex2_fma), which the sweeping warpgroup
         // leaves idle, instead of competing with it for the exp pipe
         auto sweep_chunk_fma = [&](const uint32_t (&v)[32], int c) {
-          lsum += masked ? chunk_exp<true, kPreTokenEmulate>(v, 32 * c, last_valid, m_used, pk)
-                         : chunk_exp<false, kPreTokenEmulate>(v, 32 * c, kTile, m_used, pk);
+          lsum += chunk_exp<false, kPreTokenEmulate>(v, 32 * c, kTile, m_used, pk);
           tmem_st_32x16(p_addr + 16 * c, pk);
         };
         if (kPreTokenChunks >= 1) sweep_chunk_fma(v0, 0);
@@ -359,6 +421,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         sweep_chunk(v2, 2);
         sweep_chunk(v3, 3);
         asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(256) : "memory");
+#endif
         l += lsum;
         tmem_wait_st();
         tc_fence_before();
