@@ -32,14 +32,11 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef TTASR_ATTN_PRETOKEN
 #define TTASR_ATTN_PRETOKEN 1
 #endif
-#ifndef TTASR_ATTN_PIPE
-#define TTASR_ATTN_PIPE 0
-#endif
 #ifndef TTASR_ATTN_EMUL
 #define TTASR_ATTN_EMUL 0
 #endif
+constexpr bool kEmulatePreToken = TTASR_ATTN_EMUL != 0;  // pre-token quarter: exponentials on the FMA pipe
 constexpr int kPreTokenChunks = TTASR_ATTN_PRETOKEN;  // quarters of the exp sweep done outside the token
-constexpr bool kPreTokenEmulate = TTASR_ATTN_EMUL != 0;  // ... on the FMA pipe instead of MUFU
 constexpr float kRescaleThreshold = 32.0f;  // log2 units: P stays <= 2^32 (bf16 range 2^127, O and l are fp32)
 
 // TMEM column map
@@ -58,6 +55,31 @@ struct AttnParams {
   int num_items;  // batch * heads * q_blocks
 };
 
+// Debug timeline (only with -DTTASR_ATTN_TRACE=1): CTA 0 records (tag, clock64) pairs per role into a global buffer
+// of 4 regions x cap int64 (0: MMA thread, 1/2: softmax tile 0/1 (first thread), 3: TMA producer).
+#ifndef TTASR_ATTN_TRACE
+#define TTASR_ATTN_TRACE 0
+#endif
+#if TTASR_ATTN_TRACE
+__device__ long long* g_trace_buf = nullptr;
+__device__ int g_trace_cap = 0;
+struct Tracer {
+  long long* base;
+  int n, cap;
+  __device__ Tracer(int region, bool on) : base(nullptr), n(0), cap(0) {
+    if (on && blockIdx.x == 0 && g_trace_buf) { base = g_trace_buf + static_cast<long long>(region) * g_trace_cap; cap = g_trace_cap; }
+  }
+  __device__ __forceinline__ void operator()(int tag) {
+    if (base && n + 2 <= cap) { base[n] = tag; base[n + 1] = clock64(); n += 2; }
+  }
+};
+#else
+struct Tracer {
+  __device__ Tracer(int, bool) {}
+  __device__ __forceinline__ void operator()(int) {}
+};
+#endif
+
 struct AttnSmem {
   uint8_t q[2][kTileBytes];
   uint8_t k[kKvStages][kTileBytes];
@@ -75,69 +97,46 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic for 2^f (max rel err
-// 7.7e-5, far inside P's bf16 rounding), n added into the exponent field.  x is clamped at -126 (masked = -inf -> ~0).
-// Interleaved with MUFU.EX2 on a quarter of the elements so the 16-op/clk exp pipe stops being the only limiter.
+// max over 32 fp32 values held in registers (two chains of 3-input max)
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32]) {
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    m0 = fmaxf(m0, __uint_as_float(v[2 * i]));
+    m1 = fmaxf(m1, __uint_as_float(v[2 * i + 1]));
+  }
+  return fmaxf(m0, m1);
+}
+
+// keys >= valid (tile-relative) of the 32-column chunk starting at col0 become -inf
+__device__ __forceinline__ void mask_tail(uint32_t (&v)[32], int col0, int valid) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i)
+    if (col0 + i >= valid) v[i] = 0xff800000u;
+}
+
+// p_i = 2^(s_i*log2e - m_used), written back over the scores; the row sum and the bf16 packing (sum_pack) of a chunk
+// are issued after the exponentials of the next chunk.
+__device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], float m_used) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2(fmaf(__uint_as_float(v[i]), kLog2e, -m_used)));
+}
+// 2^x on the FMA/ALU pipes (no MUFU): x = n + f with f in [-0.5, 0.5] (round-to-nearest via the 1.5*2^23 trick), cubic
+// for 2^f (max rel err 7.7e-5, far inside P's bf16 rounding), n added into the exponent field.  x is clamped at -126
+// (masked keys: -inf -> ~1e-38 ~ 0).  Used for the part of the sweep that runs beside the other warpgroup's
+// exclusive sweep, so that it does not compete for the exp pipe.
 __device__ __forceinline__ float ex2_fma(float x) {
   x = fmaxf(x, -126.0f);
-  const float xr = x + 12582912.0f;     // 1.5 * 2^23: integer part lands in the low mantissa bits
+  const float xr = x + 12582912.0f;
   const float f = x - (xr - 12582912.0f);
   float p = fmaf(0.055088683807511155f, f, 0.2426040514594791f);
   p = fmaf(p, f, 0.6932762416819607f);
   p = fmaf(p, f, 0.9999289403695112f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
 }
-
-// max over 32 fp32 values held in registers (columns col0 .. col0+31 of this thread's half row)
-template <bool MASKED>
-__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], int col0, int valid) {
-  float m0 = -INFINITY, m1 = -INFINITY;
+__device__ __forceinline__ void exp_inplace_fma(uint32_t (&v)[32], float m_used) {
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    if (!MASKED || col0 + 2 * i < valid) m0 = fmaxf(m0, __uint_as_float(v[2 * i]));
-    if (!MASKED || col0 + 2 * i + 1 < valid) m1 = fmaxf(m1, __uint_as_float(v[2 * i + 1]));
-  }
-  return fmaxf(m0, m1);
-}
-
-// p_i = 2^(s_i*log2e - m_used) for 32 columns -> 16 packed bf16 pairs; returns the fp32 sum
-template <bool MASKED, bool EMUL>
-__device__ __forceinline__ float chunk_exp(const uint32_t (&v)[32], int col0, int valid, float m_used, uint32_t (&pk)[16]) {
-  float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float x0 = __uint_as_float(v[2 * i]), x1 = __uint_as_float(v[2 * i + 1]);
-    if (MASKED) {
-      if (col0 + 2 * i >= valid) x0 = -INFINITY;
-      if (col0 + 2 * i + 1 >= valid) x1 = -INFINITY;
-    }
-    const float p0 = EMUL ? ex2_fma(fmaf(x0, kLog2e, -m_used)) : ex2(fmaf(x0, kLog2e, -m_used));
-    const float p1 = EMUL ? ex2_fma(fmaf(x1, kLog2e, -m_used)) : ex2(fmaf(x1, kLog2e, -m_used));
-    sum0 += p0;
-    sum1 += p1;
-    pk[i] = pack_bf16x2(p0, p1);
-  }
-  return sum0 + sum1;
-}
-
-__device__ __forceinline__ void mask_tail(uint32_t (&v)[32], int col0, int valid) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (col0 + i >= valid) v[i] = 0xff800000u;  // -inf
-}
-
-// Software-pipelined form of the sweep: the exponentials of a 32-column chunk are written back over the scores in
-// place (exp_inplace), and their row sum / bf16 packing (sum_pack) is issued one chunk later, so the FADD / F2FP
-// consumers never sit right behind the MUFU.EX2 that feeds them (ptxas schedules them 2 MUFUs behind, which stalls a
-// lone warp on the exp latency: 14.6 instead of 8 cycles per exponential).
-template <bool MASKED>
-__device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], int col0, int valid, float m_used) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    float x = __uint_as_float(v[i]);
-    if (MASKED && col0 + i >= valid) x = -INFINITY;
-    v[i] = __float_as_uint(ex2(fmaf(x, kLog2e, -m_used)));
-  }
+  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2_fma(fmaf(__uint_as_float(v[i]), kLog2e, -m_used)));
 }
 __device__ __forceinline__ float sum_pack(const uint32_t (&v)[32], uint32_t (&pk)[16]) {
   float sum0 = 0.f, sum1 = 0.f;
@@ -157,7 +156,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   const uint32_t pad = ((smem0 + 1023u) & ~1023u) - smem0;
   AttnSmem& s = *reinterpret_cast<AttnSmem*>(smem_raw + pad);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // warp-uniform for the compiler as well
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -186,7 +185,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&s.tmem_ptr);
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(&s.tmem_ptr), 0);
 
   auto item_coords = [&](int item, int& b, int& h, int& q0) {
     const int qb = item % p.q_blocks;
@@ -197,31 +196,43 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   };
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (whole warp walks the loop, one elected
+    // lane issues: uniform control flow keeps descriptors / addresses in uniform registers)
+    {
       int stage = 0;
       uint32_t phase = 0, qphase = 0;
+      Tracer tr(3, lane == 0);
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         int b, h, q0;
         item_coords(item, b, h, q0);
         mbar_wait(smem_u32(&s.q_free), qphase ^ 1);
         qphase ^= 1;
-        mbar_arrive_expect_tx(smem_u32(&s.q_full), 2 * kTileBytes);
-        tma_load_3d(smem_u32(&s.q[0][0]), &p.tm_qkv, smem_u32(&s.q_full), h * kHeadDim, q0, b);
-        tma_load_3d(smem_u32(&s.q[1][0]), &p.tm_qkv, smem_u32(&s.q_full), h * kHeadDim, q0 + kTile, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(smem_u32(&s.q_full), 2 * kTileBytes);
+          tma_load_3d(smem_u32(&s.q[0][0]), &p.tm_qkv, smem_u32(&s.q_full), h * kHeadDim, q0, b);
+          tma_load_3d(smem_u32(&s.q[1][0]), &p.tm_qkv, smem_u32(&s.q_full), h * kHeadDim, q0 + kTile, b);
+        }
+        __syncwarp();
         for (int j = 0; j < p.kv_tiles; ++j) {
+          tr(50);
           mbar_wait(smem_u32(&s.kv_free[stage]), phase ^ 1);
-          const uint32_t bar = smem_u32(&s.kv_full[stage]);
-          mbar_arrive_expect_tx(bar, 2 * kTileBytes);
-          tma_load_3d(smem_u32(&s.k[stage][0]), &p.tm_qkv, bar, p.d_model + h * kHeadDim, j * kTile, b);
-          tma_load_3d(smem_u32(&s.v[stage][0]), &p.tm_qkv, bar, 2 * p.d_model + h * kHeadDim, j * kTile, b);
+          tr(51);
+          if (elect_one()) {
+            const uint32_t bar = smem_u32(&s.kv_full[stage]);
+            mbar_arrive_expect_tx(bar, 2 * kTileBytes);
+            tma_load_3d(smem_u32(&s.k[stage][0]), &p.tm_qkv, bar, p.d_model + h * kHeadDim, j * kTile, b);
+            tma_load_3d(smem_u32(&s.v[stage][0]), &p.tm_qkv, bar, 2 * p.d_model + h * kHeadDim, j * kTile, b);
+          }
+          __syncwarp();
           if (++stage == kKvStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================== MMA issuer (uniform control flow, one elected lane
+    // issues: each tcgen05.mma is then a single UTCHMMA on precomputed uniform registers instead of a per-instruction
+    // elect/waterfall sequence that starves behind the softmax warps of the same scheduler)
+    {
       constexpr uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, 0, 0);      // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = umma_idesc_bf16(kTile, kHeadDim, 0, 1);   // P (tmem)   x V (MN-major)
       int stage = 0;            // stage of KV tile j+1 (S look-ahead)
@@ -231,31 +242,53 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       auto issue_s = [&](int t, int st) {
         const uint64_t adesc = umma_desc_sw128(smem_u32(&s.q[t][0]), 16, 1024);
         const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.k[st][0]), 16, 1024);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kHeadDim / 16; ++k)
-          umma_ss<1>(tmem_base + kColS + t * kTile, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-        umma_commit(smem_u32(&s.s_full[t]));
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_ss<1>(tmem_base + kColS + t * kTile, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&s.s_full[t]));
+        }
+        __syncwarp();
+      };
+      auto commit = [&](unsigned long long* bar) {
+        if (elect_one()) umma_commit(smem_u32(bar));
+        __syncwarp();
       };
       uint32_t fphase[2] = {0, 0};
+      Tracer tr(0, lane == 0);
       // O_t (+)= P_t V : V tile is [128 keys][64] row-major = MN-major B operand, 16 keys per MMA
       auto issue_pv = [&](int t, int st, bool first, bool last) {
         const uint64_t vdesc = umma_desc_sw128(smem_u32(&s.v[st][0]), kTileBytes, 1024);
+        if (elect_one()) {
+          tr(60);
 #pragma unroll
-        for (int k = 0; k < kTile / 16; ++k)
-          umma_ts(tmem_base + kColO + t * kHeadDim, tmem_base + kColP + t * 64 + k * 8, vdesc + 128 * k, idesc_o,
-                  (first && k == 0) ? 0u : 1u);
-        umma_commit(smem_u32(&s.o_done[t]));  // per-PV completion: P_t consumed, O_t quiescent
+          for (int k = 0; k < kTile / 16; ++k) {
+            umma_ts(tmem_base + kColO + t * kHeadDim, tmem_base + kColP + t * 64 + k * 8, vdesc + 128 * k, idesc_o,
+                    (first && k == 0) ? 0u : 1u);
+            if (k == 0) tr(61);
+            if (k == 3) tr(62);
+          }
+          tr(63);
+          umma_commit(smem_u32(&s.o_done[t]));  // per-PV completion: P_t consumed, O_t quiescent
+          tr(64);
+        }
+        __syncwarp();
+        tr(65);
         (void)last;
       };
       auto wait_p = [&](int t) {
+        tr(30 + t);
         mbar_wait(smem_u32(&s.p_ready[t]), pphase[t]);
         pphase[t] ^= 1;
         tc_fence_after();
+        tr(32 + t);
       };
       auto wait_sfree = [&](int t) {
+        tr(40 + t);
         mbar_wait(smem_u32(&s.s_free[t]), fphase[t]);
         fphase[t] ^= 1;
         tc_fence_after();
+        tr(42 + t);
       };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         mbar_wait(smem_u32(&s.q_full), qphase);
@@ -264,7 +297,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tc_fence_after();
         issue_s(0, stage);
         issue_s(1, stage);
-        if (p.kv_tiles == 1) umma_commit(smem_u32(&s.q_free));
+        if (p.kv_tiles == 1) commit(&s.q_free);
         int cur = stage;   // stage of KV tile j
         int prev = stage;  // stage of KV tile j-1
         if (++stage == kKvStages) { stage = 0; phase ^= 1; }
@@ -274,8 +307,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         for (int j = 0; j < p.kv_tiles; ++j) {
           const bool more = (j + 1 < p.kv_tiles);
           if (more) {
+            tr(44);
             mbar_wait(smem_u32(&s.kv_full[stage]), phase);
             tc_fence_after();
+            tr(45);
             wait_sfree(0);
             issue_s(0, stage);
           } else {
@@ -284,12 +319,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           if (j > 0) {
             wait_p(1);
             issue_pv(1, prev, j == 1, false);
-            umma_commit(smem_u32(&s.kv_free[prev]));  // every MMA that read KV tile j-1 has been issued
+            commit(&s.kv_free[prev]);  // every MMA that read KV tile j-1 has been issued
           }
           if (more) {
             wait_sfree(1);
             issue_s(1, stage);
-            if (j + 2 == p.kv_tiles) umma_commit(smem_u32(&s.q_free));  // last S of the item issued
+            if (j + 2 == p.kv_tiles) commit(&s.q_free);  // last S of the item issued
           } else {
             wait_sfree(1);
           }
@@ -303,7 +338,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
         wait_p(1);
         issue_pv(1, prev, p.kv_tiles == 1, true);
-        umma_commit(smem_u32(&s.kv_free[prev]));
+        commit(&s.kv_free[prev]);
       }
     }
   } else if (warp >= 4) {
@@ -319,6 +354,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     constexpr uint32_t kTokBar = 2;         // +t: warpgroup t may start its exp sweep (the other one has finished its own)
     constexpr uint32_t kEpiBar = 4;         // +t: warpgroup-local barrier of the output staging
     uint32_t sphase = 0, ophase = 0;
+    Tracer tr(1 + t, wq == 0 && lane == 0);
     const int last_valid = p.n_ctx - (p.kv_tiles - 1) * kTile;  // valid keys in the last KV tile
     const bool last_masked = last_valid < kTile;
     if (t == 1) asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + 0), "r"(256) : "memory");  // warpgroup 0 sweeps first
@@ -329,15 +365,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       float l = 0.f;
       for (int j = 0; j < p.kv_tiles; ++j) {
         const bool masked = last_masked && (j == p.kv_tiles - 1);
+        tr(10);
         mbar_wait(smem_u32(&s.s_full[t]), sphase);
         sphase ^= 1;
         tc_fence_after();
+        tr(11);
         uint32_t v0[32], v1[32], v2[32], v3[32];
         tmem_ld_32x32(s_addr, v0);
         tmem_ld_32x32(s_addr + 32, v1);
         tmem_ld_32x32(s_addr + 64, v2);
         tmem_ld_32x32(s_addr + 96, v3);
         tmem_wait_ld();
+        tr(12);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s.s_free[t]));  // S_t is in registers: the next S_t may be produced now
@@ -347,14 +386,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           mask_tail(v2, 64, last_valid);
           mask_tail(v3, 96, last_valid);
         }
-        const float mx = fmaxf(fmaxf(chunk_max<false>(v0, 0, kTile), chunk_max<false>(v1, 32, kTile)),
-                               fmaxf(chunk_max<false>(v2, 64, kTile), chunk_max<false>(v3, 96, kTile)));
+        const float mx = fmaxf(fmaxf(chunk_max(v0), chunk_max(v1)), fmaxf(chunk_max(v2), chunk_max(v3)));
         const float m_tile = mx * kLog2e;
-        if (j > 0) {  // PV_t(j-1) (issued a sweep ago) has consumed P_t and finished accumulating into O_t
+        tr(13);
+        // PV_t(j-1) (issued a sweep ago) must have consumed P_t and left O_t quiescent before either is written again.
+        // (Deferring this wait into the sweep was measured slower: it then sits inside the token-exclusive section.)
+        if (j > 0) {
           mbar_wait(smem_u32(&s.o_done[t]), ophase);
           ophase ^= 1;
           tc_fence_after();
         }
+        tr(14);
         if (j == 0) {
           m_used = m_tile;
         } else if (__any_sync(0xffffffffu, (m_tile - m_used) > kRescaleThreshold)) {  // rare
@@ -374,20 +416,21 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
         // ---- exp sweep.  The first kPreTokenChunks quarter(s) run beside the other warpgroup's sweep (one warp per
         // scheduler cannot quite saturate the 16-op/clk exp pipe); the rest is exclusive (token), so the pipe never
-        // idles while this warpgroup waits for / reads its next S tile.
-#if TTASR_ATTN_PIPE
+        // idles while this warpgroup waits for / reads its next S tile.  The exponentials go back over the scores in
+        // place; the row sum / bf16 packing / P store of a quarter follow the exponentials of the next one.
         uint32_t pk[16];
         float lsum = 0.f;
         auto stage_a = [&](uint32_t (&v)[32], int c) {
-          exp_inplace<false>(v, 32 * c, kTile, m_used);
+          exp_inplace(v, m_used);
         };
         auto stage_b = [&](const uint32_t (&v)[32], int c) {
           lsum += sum_pack(v, pk);
           tmem_st_32x16(p_addr + 16 * c, pk);
         };
-        auto tok_acquire = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory"); };
+        auto tok_acquire = [&]() { tr(15); asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory"); tr(16); };
         if (kPreTokenChunks == 0) tok_acquire();
-        stage_a(v0, 0);
+        if (kPreTokenChunks >= 1 && kEmulatePreToken) exp_inplace_fma(v0, m_used);
+        else stage_a(v0, 0);
         if (kPreTokenChunks == 1) tok_acquire();
         stage_a(v1, 1);
         stage_b(v0, 0);
@@ -400,36 +443,18 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(256) : "memory");  // last exp issued
         stage_b(v2, 2);
         stage_b(v3, 3);
-#else
-        uint32_t pk[16];
-        float lsum = 0.f;
-        auto sweep_chunk = [&](const uint32_t (&v)[32], int c) {
-          lsum += chunk_exp<false, false>(v, 32 * c, kTile, m_used, pk);
-          tmem_st_32x16(p_addr + 16 * c, pk);
-        };
-        // outside the token the exponentials go through the FMA/ALU pipes (ex2_fma), which the sweeping warpgroup
-        // leaves idle, instead of competing with it for the exp pipe
-        auto sweep_chunk_fma = [&](const uint32_t (&v)[32], int c) {
-          lsum += chunk_exp<false, kPreTokenEmulate>(v, 32 * c, kTile, m_used, pk);
-          tmem_st_32x16(p_addr + 16 * c, pk);
-        };
-        if (kPreTokenChunks >= 1) sweep_chunk_fma(v0, 0);
-        if (kPreTokenChunks >= 2) sweep_chunk_fma(v1, 1);
-        asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory");
-        if (kPreTokenChunks < 1) sweep_chunk(v0, 0);
-        if (kPreTokenChunks < 2) sweep_chunk(v1, 1);
-        sweep_chunk(v2, 2);
-        sweep_chunk(v3, 3);
-        asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(256) : "memory");
-#endif
         l += lsum;
+        tr(17);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&s.p_ready[t]));
+        tr(18);
       }
       // ---- epilogue: O / l -> bf16 -> swizzled smem -> TMA store
+      tr(20);
       mbar_wait(smem_u32(&s.o_done[t]), ophase);
+      tr(21);
       ophase ^= 1;
       tc_fence_after();
       if (leader) tma_store_wait_read<0>();  // staging tile of the previous item has been read out
@@ -460,6 +485,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tma_store_3d(&p.tm_out, smem_u32(&s.o[t][0]), h * kHeadDim, q0 + t * kTile, b);
         tma_store_commit();
       }
+      tr(22);
     }
     if (t == 0) asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + 0), "r"(256) : "memory");  // absorb the last token
     if (leader) tma_store_wait<0>();
@@ -471,6 +497,14 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
 }
 
 }  // namespace
+
+#if TTASR_ATTN_TRACE
+extern "C" __attribute__((visibility("default"))) int ttasr_debug_attention_trace(long long* buf_dev, int cap) {
+  cudaError_t e = cudaMemcpyToSymbol(g_trace_buf, &buf_dev, sizeof(buf_dev));
+  if (e == cudaSuccess) e = cudaMemcpyToSymbol(g_trace_cap, &cap, sizeof(cap));
+  return e == cudaSuccess ? 0 : -1;
+}
+#endif
 
 cudaError_t attention_launch(const void* qkv, void* out, int batch, int n_ctx, int n_heads, int num_sms,
                              cudaStream_t stream, const char** why) {
