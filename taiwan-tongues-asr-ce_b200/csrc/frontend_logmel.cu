@@ -1,9 +1,14 @@
 // Fused Whisper log-mel front end for sm_100a.
 //
 //   kernel 1  logmel_frames_kernel : PCM -> framing (centre/reflect) -> Hann -> 400-pt FFT -> |.|^2 -> sparse mel
-//                                    -> max(1e-10, .) -> log10 -> raw log-mel [B, n_mels, T] + per-chunk max
-//   kernel 2  logmel_finalize_kernel: max(x, chunk_max - 8), (x + 4) / 4 in place; optional bf16 time-major copy
-//                                    [B, T, n_mels] for the conv stem's implicit GEMM.
+//                                    -> max(1e-10, .) -> log10 -> y = (x + 4) / 4 written once, as fp32 [B, n_mels, T]
+//                                    and (optionally) as the bf16 time-major copy [B, T, ld] the conv stem's implicit
+//                                    GEMM reads; per-chunk max (atomic) and per-tile min on the side.
+//   kernel 2  logmel_clamp_kernel  : the reference's max(x, chunk_max - 8) is max(y, y_max - 2) after the affine map
+//                                    (both monotone), so only tiles whose minimum lies below y_max - 2 are touched
+//                                    again, plus the all-padding tiles kernel 1 skipped (one constant fill).  On
+//                                    ordinary audio (dynamic range < 8 decades inside a tile) this pass reads two
+//                                    small tables and exits: every feature byte is written to HBM exactly once.
 //
 // Reference semantics: HF WhisperFeatureExtractor._np_extract_fbank_features
 // (transformers/models/whisper/feature_extraction_whisper.py:105-133, audio_utils.py:624-832), the extractor the
@@ -44,6 +49,7 @@ struct __align__(16) FrontSmem {
   int mel_lo[kMaxMels];
   int mel_cnt[kMaxMels];
   int mel_off[kMaxMels];
+  float wmin[kThreads / 32];
   unsigned long long bar;
 };
 
@@ -56,18 +62,24 @@ __device__ __forceinline__ float load_sample<int16_t>(const float* buf, int i) {
   return static_cast<float>(reinterpret_cast<const int16_t*>(buf)[i]) * (1.0f / 32768.0f);
 }
 
-__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  if (v >= 0.f)
-    atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
-  else
-    atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+// order-preserving float -> uint map, so that a zero-filled (cudaMemsetAsync) word is below every float and
+// atomicMax on the encoded value is a float max
+__device__ __forceinline__ unsigned enc_ordered(float v) {
+  const unsigned b = __float_as_uint(v);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
+__device__ __forceinline__ float dec_ordered(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+constexpr float kYFloor = -1.5f;                         // (log10(1e-10) + 4) / 4
+constexpr float kLog2ToY = 0.25f * 0.30102999566398120f; // y = log2(p) * log10(2) / 4 + 1
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
 logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int* __restrict__ n_valid, int n_samples,
                      int n_frames, int n_mels, int batch, FrontTables tables, float* __restrict__ raw,
-                     float* __restrict__ chunk_max) {
+                     unsigned* __restrict__ chunk_max, float* __restrict__ tile_min, __nv_bfloat16* __restrict__ tmajor,
+                     int tmajor_ld) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FrontSmem& s = *reinterpret_cast<FrontSmem*>(smem_raw);
   const int tid = threadIdx.x;
@@ -144,15 +156,13 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
     int b, tt, valid;
     classify(tile, b, tt, valid);
     const int t0 = tt * kTileFrames;
-    float tmax = -INFINITY;
+    float tmax = -INFINITY, tmin = INFINITY;
 
     if (kind_cur == 0) {
-      // every sample the tile touches is zero padding: mel power 0 -> floor
-      for (int idx = tid; idx < kTileFrames * n_mels; idx += kThreads) {
-        const int f = idx % kTileFrames, m = idx / kTileFrames;
-        if (t0 + f < n_frames) raw[(static_cast<long long>(b) * n_mels + m) * n_frames + t0 + f] = kLog10Floor;
-      }
-      tmax = kLog10Floor;
+      // every sample the tile touches is zero padding: mel power 0 -> floor.  Nothing is written here; the clamp
+      // kernel fills the tile with max(floor, y_max - 2) in one go (tile_min = -inf marks "not written").
+      tmax = kYFloor;
+      tmin = -INFINITY;
       if (next < total_tiles) kind_next = stage(next);  // staging buffer is idle on this path
     } else {
       if (kind_cur == 1) {
@@ -242,76 +252,112 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         const int lane = tid & 31;
         const bool live = (t0 + lane) < n_frames;
         float* out_col = raw + static_cast<long long>(b) * n_mels * n_frames + t0 + lane;
+        __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2);  // ti is idle by now
         for (int m = tid >> 5; m < n_mels; m += kThreads / 32) {
           const float* pwm = &s.tr[s.mel_lo[m] * kPwPitch + lane];
           const float* w = &s.melw[s.mel_off[m]];
           const int cnt = s.mel_cnt[m];
           float acc = 0.f;
           for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], pwm[j * kPwPitch], acc);
-          // log10 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate); the floor is returned exactly
-          const float v = acc > kMelFloor ? __log2f(acc) * 0.30102999566398120f : kLog10Floor;
+          // (log10 + 4) / 4 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate); the floor is returned exactly
+          const float v = acc > kMelFloor ? fmaf(__log2f(acc), kLog2ToY, 1.0f) : kYFloor;
           if (live) {
             out_col[static_cast<long long>(m) * n_frames] = v;
             tmax = fmaxf(tmax, v);
+            tmin = fminf(tmin, v);
           }
+          if (tmajor) stg[m] = __float2bfloat16_rn(v);
         }
       }
-      __syncthreads();  // power spectra consumed before the next tile's pass 1 overwrites the buffer
+      __syncthreads();  // power spectra consumed before the next tile's pass 1 overwrites the buffer; staging complete
+      if (tmajor) {
+        // [t][m] bf16 rows, channels contiguous and zero-padded to tmajor_ld: 4-byte words, coalesced per frame
+        const int wpr = tmajor_ld >> 1;                     // words per row
+        const uint32_t* stw = reinterpret_cast<const uint32_t*>(&s.ti[0]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(tmajor + (static_cast<long long>(b) * n_frames + t0) * tmajor_ld);
+        const int nrows = min(kTileFrames, n_frames - t0);
+        for (int idx = tid; idx < nrows * wpr; idx += kThreads) {
+          const int f = idx / wpr, wi = idx - f * wpr;
+          uint32_t v = stw[f * (wpr + 1) + wi];
+          if (2 * wi + 1 >= n_mels) v = (2 * wi < n_mels) ? (v & 0xffffu) : 0u;
+          dst[static_cast<long long>(f) * wpr + wi] = v;
+        }
+        // (the next writer of ti is the next tile's pass 1, behind the block barrier of the tile-min reduction below)
+      }
     }
-    // ---------------- tile max -> chunk max (one atomic per warp)
+    // ---------------- tile max -> chunk max (one atomic per warp); tile min -> table (one store per tile)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-    if ((tid & 31) == 0 && tmax > -INFINITY) atomic_max_float(&chunk_max[b], tmax);
+    for (int o = 16; o > 0; o >>= 1) {
+      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
+      tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    }
+    if ((tid & 31) == 0) {
+      if (tmax > -INFINITY) atomicMax(&chunk_max[b], enc_ordered(tmax));
+      s.wmin[tid >> 5] = tmin;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      float m = s.wmin[0];
+#pragma unroll
+      for (int w = 1; w < kThreads / 32; ++w) m = fminf(m, s.wmin[w]);
+      tile_min[static_cast<long long>(b) * tiles_per_chunk + tt] = m;
+    }
     kind_cur = kind_next;
   }
 }
 
-// clamp + affine (+ bf16 time-major copy).  One CTA: 32 frames x all mels of one chunk.
+// Second pass, normally a no-op: CTA (x, b) looks at kClampTiles tiles of chunk b and rewrites only those whose
+// minimum is below y_max - 2 (clamp) or that kernel 1 left unwritten (all-padding tiles: constant fill).
+constexpr int kClampTiles = 8;
 __global__ void __launch_bounds__(256)
-logmel_finalize_kernel(float* __restrict__ feats, const float* __restrict__ chunk_max, int n_frames, int n_mels,
-                       __nv_bfloat16* __restrict__ tmajor, int tmajor_ld) {
+logmel_clamp_kernel(float* __restrict__ feats, const unsigned* __restrict__ chunk_max, const float* __restrict__ tile_min,
+                    int n_frames, int n_mels, int tiles_per_chunk, __nv_bfloat16* __restrict__ tmajor, int tmajor_ld) {
   __shared__ float tile[kMaxMels][33];
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * 32;
-  const float lo = chunk_max[b] - 8.0f;
+  const float lo = dec_ordered(chunk_max[b]) - 2.0f;
   float* base = feats + static_cast<long long>(b) * n_mels * n_frames;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  for (int m = wrp; m < n_mels; m += 8) {
+  const int wpr = tmajor_ld >> 1;  // 4-byte words per bf16 row
+  const int tile_end = min((blockIdx.x + 1) * kClampTiles, tiles_per_chunk);
+  for (int tt = blockIdx.x * kClampTiles; tt < tile_end; ++tt) {
+    const float tmin = tile_min[static_cast<long long>(b) * tiles_per_chunk + tt];
+    if (tmin >= lo) continue;                       // the common case: nothing below the clamp
+    const bool unwritten = (tmin == -INFINITY);
+    const int t0 = tt * kTileFrames;
     const int t = t0 + lane;
-    float v = 0.f;
-    if (t < n_frames) {
-      v = base[static_cast<long long>(m) * n_frames + t];
-      v = (fmaxf(v, lo) + 4.0f) * 0.25f;
-      base[static_cast<long long>(m) * n_frames + t] = v;
+    const float fillv = fmaxf(kYFloor, lo);
+    for (int m = wrp; m < n_mels; m += 8) {         // lanes = frames: 128-byte segments along time
+      float v = fillv;
+      if (t < n_frames) {
+        float* ptr = base + static_cast<long long>(m) * n_frames + t;
+        if (!unwritten) v = fmaxf(*ptr, lo);
+        *ptr = v;
+      }
+      tile[m][lane] = v;
     }
-    tile[m][lane] = v;
+    if (tmajor) {                                   // rewrite the bf16 rows of the tile, channels contiguous
+      __syncthreads();
+      uint32_t* dst = reinterpret_cast<uint32_t*>(tmajor + (static_cast<long long>(b) * n_frames + t0) * tmajor_ld);
+      const int nrows = min(kTileFrames, n_frames - t0);
+      for (int idx = threadIdx.x; idx < nrows * wpr; idx += 256) {
+        const int f = idx / wpr, mp = (idx - f * wpr) * 2;
+        const float v0 = mp < n_mels ? tile[mp][f] : 0.f;
+        const float v1 = mp + 1 < n_mels ? tile[mp + 1][f] : 0.f;
+        dst[idx] = pack_bf16x2(v0, v1);
+      }
+      __syncthreads();                              // tile[] is reused by the next flagged tile
+    }
   }
-  if (tmajor == nullptr) return;
-  __syncthreads();
-  // [t][m] bf16, channels contiguous (zero for m >= n_mels up to tmajor_ld)
-  for (int idx = threadIdx.x; idx < 32 * (tmajor_ld / 2); idx += 256) {
-    const int f = idx / (tmajor_ld / 2), mp = (idx % (tmajor_ld / 2)) * 2;
-    const int t = t0 + f;
-    if (t >= n_frames) continue;
-    const float v0 = mp < n_mels ? tile[mp][f] : 0.f;
-    const float v1 = mp + 1 < n_mels ? tile[mp + 1][f] : 0.f;
-    reinterpret_cast<uint32_t*>(tmajor + (static_cast<long long>(b) * n_frames + t) * tmajor_ld)[mp / 2] =
-        pack_bf16x2(v0, v1);
-  }
-}
-
-__global__ void fill_kernel(float* p, int n, float v) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
 }
 
 }  // namespace
 
 size_t frontend_smem_bytes() { return sizeof(FrontSmem); }
+int frontend_tiles(int n_samples) { return (n_samples / kHop + kTileFrames - 1) / kTileFrames; }
 
 cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
-                          int n_mels, int batch, const FrontTables& tables, float* feats, float* chunk_max,
-                          __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream) {
+                          int n_mels, int batch, const FrontTables& tables, float* feats, unsigned* chunk_max,
+                          float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream) {
   const int n_frames = n_samples / kHop;
   const int tiles_per_chunk = (n_frames + kTileFrames - 1) / kTileFrames;
   const long long total = static_cast<long long>(batch) * tiles_per_chunk;
@@ -324,18 +370,24 @@ cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride,
     e = cudaFuncSetAttribute(logmel_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  fill_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(chunk_max, batch, -INFINITY);
+  if (tmajor && static_cast<size_t>(kTileFrames) * (tmajor_ld + 2) * sizeof(__nv_bfloat16) > sizeof(FrontSmem::ti))
+    return cudaErrorInvalidValue;
+  {
+    cudaError_t e = cudaMemsetAsync(chunk_max, 0, sizeof(unsigned) * batch, stream);  // 0 < enc_ordered(any float)
+    if (e != cudaSuccess) return e;
+  }
   const int grid = static_cast<int>(total < 2LL * num_sms ? total : 2LL * num_sms);
   if (pcm_is_i16)
     logmel_frames_kernel<int16_t><<<grid, kThreads, smem, stream>>>(static_cast<const int16_t*>(pcm), row_stride, n_valid,
                                                                    n_samples, n_frames, n_mels, batch, tables, feats,
-                                                                   chunk_max);
+                                                                   chunk_max, tile_min, tmajor, tmajor_ld);
   else
     logmel_frames_kernel<float><<<grid, kThreads, smem, stream>>>(static_cast<const float*>(pcm), row_stride, n_valid,
                                                                  n_samples, n_frames, n_mels, batch, tables, feats,
-                                                                 chunk_max);
-  dim3 g2((n_frames + 31) / 32, batch);
-  logmel_finalize_kernel<<<g2, 256, 0, stream>>>(feats, chunk_max, n_frames, n_mels, tmajor, tmajor_ld);
+                                                                 chunk_max, tile_min, tmajor, tmajor_ld);
+  dim3 g2((tiles_per_chunk + kClampTiles - 1) / kClampTiles, batch);
+  logmel_clamp_kernel<<<g2, 256, 0, stream>>>(feats, chunk_max, tile_min, n_frames, n_mels, tiles_per_chunk, tmajor,
+                                              tmajor_ld);
   return cudaGetLastError();
 }
 

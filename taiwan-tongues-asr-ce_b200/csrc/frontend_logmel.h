@@ -24,7 +24,9 @@ size_t frontend_smem_bytes();
 // feats: [B, n_mels, n_samples/160] fp32 (HF layout).  tmajor (optional): [B, T, tmajor_ld] bf16, zero-padded channels.
 // n_valid (optional, device): samples >= n_valid[b] are treated as zero and never read.
 cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
-                          int n_mels, int batch, const FrontTables& tables, float* feats, float* chunk_max,
-                          __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream);
+                          int n_mels, int batch, const FrontTables& tables, float* feats, unsigned* chunk_max,
+                          float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream);
+// scratch the caller provides: chunk_max[batch] (order-encoded running maxima), tile_min[batch * frontend_tiles(n_samples)]
+int frontend_tiles(int n_samples);
 
 }  // namespace ttasr

@@ -94,7 +94,8 @@ struct ttasr_frontend {
   int n_samples = 0;
   FrontTables tables{};
   void* table_mem = nullptr;
-  float* chunk_max = nullptr;  // per-chunk running maxima, capacity max_batch
+  unsigned* chunk_max = nullptr;  // per-chunk running maxima (order-encoded), capacity max_batch
+  float* tile_min = nullptr;      // per-tile minima, capacity max_batch * tiles per chunk
   int64_t max_batch = 0;
 };
 
@@ -165,11 +166,14 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
   h->tables.mel_lo = static_cast<const int*>(put(lo.data(), sizeof(int) * kMaxMels));
   h->tables.mel_cnt = static_cast<const int*>(put(cnt.data(), sizeof(int) * kMaxMels));
   h->tables.mel_off = static_cast<const int*>(put(off.data(), sizeof(int) * kMaxMels));
-  h->max_batch = 1 << 16;
-  e = cudaMalloc(&h->chunk_max, sizeof(float) * h->max_batch);
+  h->max_batch = 1 << 14;
+  e = cudaMalloc(&h->chunk_max, sizeof(unsigned) * h->max_batch);
+  if (e == cudaSuccess) e = cudaMalloc(&h->tile_min, sizeof(float) * h->max_batch * frontend_tiles(n_samples));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     cudaFree(h->table_mem);
+    cudaFree(h->chunk_max);
+    cudaFree(h->tile_min);
     delete h;
     return fail(TTASR_E_CUDA, "frontend_create: %s", cudaGetErrorString(e));
   }
@@ -193,7 +197,7 @@ int ttasr_frontend_run(const ttasr_frontend_t* h, const void* pcm_dev, int pcm_d
   if (!n_valid_dev && row_stride < h->n_samples) return fail(TTASR_E_SHAPE, "frontend_run: row_stride %lld < n_samples %d without n_valid", (long long)row_stride, h->n_samples);
   if (tmajor_dev && (tmajor_ld < h->n_mels || (tmajor_ld & 1))) return fail(TTASR_E_SHAPE, "frontend_run: tmajor_ld must be even and >= n_mels");
   cudaError_t e = launch_logmel(pcm_dev, pcm_dtype == TTASR_PCM_I16, row_stride, n_valid_dev, h->n_samples, h->n_mels,
-                                static_cast<int>(batch), h->tables, feats_dev, h->chunk_max,
+                                static_cast<int>(batch), h->tables, feats_dev, h->chunk_max, h->tile_min,
                                 static_cast<__nv_bfloat16*>(tmajor_dev), tmajor_ld, h->num_sms,
                                 static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(TTASR_E_CUDA, "frontend_run: launch failed: %s", cudaGetErrorString(e));
@@ -204,6 +208,7 @@ void ttasr_frontend_destroy(ttasr_frontend_t* h) {
   if (!h) return;
   cudaFree(h->table_mem);
   cudaFree(h->chunk_max);
+  cudaFree(h->tile_min);
   delete h;
 }
 

@@ -181,7 +181,9 @@ class B200WhisperFeatureExtractor:
                 host[i, lengths[i]:] = self.padding_value
         dev = self._torch_device() if device in (None, "cpu") else torch.device(device)
         pcm = torch.from_numpy(host).to(dev, non_blocking=False)
-        feats = self.extract(pcm)
+        # right padding with 0.0 is what n_valid means to the kernel: padded tiles skip the transform altogether
+        n_valid = torch.from_numpy(lengths).to(dev) if (self.padding_value == 0.0 and not do_normalize) else None
+        feats = self.extract(pcm, n_valid=n_valid)
         out = _BatchFeature({"input_features": feats.cpu().numpy()})
         if return_attention_mask:
             out["attention_mask"] = mask[:, :: self.hop_length]

@@ -101,3 +101,32 @@ def test_reference_call_surface(cuda_device):
     assert out.get("attention_mask")[0].shape == (3000,) and out["attention_mask"][0].sum() == 300
     with pytest.raises(ValueError):
         fe(x, sampling_rate=8000)
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_clamp_pass_paths_f32_and_time_major(cuda_device, n_mels):
+    """The second kernel only touches tiles below max - 8 (in-data silence, large dynamic range) and the padding tiles
+    the first kernel skipped (n_valid): both the fp32 features and the bf16 time-major copy must carry the clamp."""
+    import torch
+
+    rng = np.random.default_rng(11)
+    loud = (0.3 * rng.standard_normal(OF.N_SAMPLES)).astype(np.float32)
+    a = loud.copy()
+    a[100_000:300_000] = 0.0                       # digital silence inside the clip (stays a "written" tile)
+    b = loud.copy()
+    b[200_000:] *= 1e-5                            # 100 dB quieter tail: values below the clamp, not constant
+    c = OF.pad_or_trim(loud[:50_000])              # short clip, padding given as n_valid
+    clips = [a, b, c]
+    pcm = torch.from_numpy(np.stack(clips)).to(cuda_device)
+    nv = torch.tensor([OF.N_SAMPLES, OF.N_SAMPLES, 50_000], dtype=torch.int32, device=cuda_device)
+    fe = _fe(n_mels)
+    feats, tm = fe.extract(pcm, n_valid=nv, return_time_major=True)
+    feats, tm = feats.cpu().numpy(), tm.float().cpu().numpy()
+    for i, clip in enumerate(clips):
+        ref = OF.log_mel(clip, n_mels)
+        assert np.abs(feats[i] - ref).max() <= TOL, f"clip {i}"
+        assert ref.min() == pytest.approx(ref.max() - 2.0, abs=1e-5)   # the clamp is active in every clip
+        # bf16 copy = rounding of the final fp32 features, channels zero-padded
+        want = torch.from_numpy(feats[i].T.copy()).to(torch.bfloat16).float().numpy()
+        assert np.array_equal(tm[i, :, :n_mels], want), f"clip {i}: time-major copy differs from the fp32 features"
+        assert np.all(tm[i, :, n_mels:] == 0)
