@@ -109,9 +109,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
   const bool rows_aligned = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((row_stride * sizeof(T)) % 16 == 0);
 
   // tile classification: 0 = all-zero (skip the transform), 1 = interior (bulk copy), 2 = edge (reflect / zero fill)
-  auto classify = [&](long long tile, int& b, int& tt, int& valid) -> int {
-    b = static_cast<int>(tile / tiles_per_chunk);
-    tt = static_cast<int>(tile % tiles_per_chunk);
+  auto classify = [&](int b, int tt, int& valid) -> int {
     valid = n_valid ? min(max(n_valid[b], 0), n_samples) : n_samples;
     valid = static_cast<int>(min(static_cast<long long>(valid), row_stride));  // never read past the row
     const int start = tt * kTileFrames * kHop - kNfft / 2;
@@ -120,9 +118,9 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
     return 2;
   };
   // bring a tile's PCM span into the staging buffer (asynchronously when interior); caller guarantees it is free
-  auto stage = [&](long long tile) -> int {
-    int b, tt, valid;
-    const int kind = classify(tile, b, tt, valid);
+  auto stage = [&](int b, int tt) -> int {
+    int valid;
+    const int kind = classify(b, tt, valid);
     const int start = tt * kTileFrames * kHop - kNfft / 2;
     const T* row = pcm + static_cast<long long>(b) * row_stride;
     if (kind == 1) {
@@ -145,16 +143,19 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
     return kind;
   };
 
+  // tiles are walked with stride gridDim.x; (chunk, tile-in-chunk) advance incrementally (no 64-bit division per tile)
+  const int step_b = static_cast<int>(gridDim.x) / tiles_per_chunk, step_t = static_cast<int>(gridDim.x) % tiles_per_chunk;
   uint32_t phase = 0;
   long long tile = blockIdx.x;
+  int b = static_cast<int>(blockIdx.x) / tiles_per_chunk, tt = static_cast<int>(blockIdx.x) % tiles_per_chunk;
   int kind_cur = 0;
-  if (tile < total_tiles) kind_cur = stage(tile);
+  if (tile < total_tiles) kind_cur = stage(b, tt);
 
   for (; tile < total_tiles; tile += gridDim.x) {
     const long long next = tile + gridDim.x;
+    int b_next = b + step_b, tt_next = tt + step_t;
+    if (tt_next >= tiles_per_chunk) { tt_next -= tiles_per_chunk; ++b_next; }
     int kind_next = 0;
-    int b, tt, valid;
-    classify(tile, b, tt, valid);
     const int t0 = tt * kTileFrames;
     float tmax = -INFINITY, tmin = INFINITY;
 
@@ -163,7 +164,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
       // kernel fills the tile with max(floor, y_max - 2) in one go (tile_min = -inf marks "not written").
       tmax = kYFloor;
       tmin = -INFINITY;
-      if (next < total_tiles) kind_next = stage(next);  // staging buffer is idle on this path
+      if (next < total_tiles) kind_next = stage(b_next, tt_next);  // staging buffer is idle on this path
     } else {
       if (kind_cur == 1) {
         mbar_wait(bar, phase);
@@ -196,7 +197,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
       }
       __syncthreads();
       // the PCM span is consumed: fetch the next tile's span under passes 2..4
-      if (next < total_tiles) kind_next = stage(next);
+      if (next < total_tiles) kind_next = stage(b_next, tt_next);
       // ---------------- pass 2: thread (grp, k1) transforms over n2 -> Z[k1 + 20 k2]
       {
         float xr[20], xi[20], yr[20], yi[20];
@@ -303,6 +304,8 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
       tile_min[static_cast<long long>(b) * tiles_per_chunk + tt] = m;
     }
     kind_cur = kind_next;
+    b = b_next;
+    tt = tt_next;
   }
 }
 
