@@ -55,6 +55,7 @@ enum { TTASR_OUT_BF16 = 0, TTASR_OUT_F32 = 1 };
 
 typedef struct ttasr_frontend ttasr_frontend_t;
 typedef struct ttasr_encoder ttasr_encoder_t;
+typedef struct ttasr_ingest ttasr_ingest_t;
 
 TTASR_API int ttasr_abi_version(void);
 TTASR_API const char* ttasr_last_error(void);
@@ -79,6 +80,23 @@ TTASR_API int ttasr_frontend_run(const ttasr_frontend_t* h, const void* pcm_dev,
 /* bytes of scratch (per-chunk maxima) the handle keeps per batch element; informational */
 TTASR_API int ttasr_frontend_max_batch(const ttasr_frontend_t* h, int64_t* out);
 TTASR_API void ttasr_frontend_destroy(ttasr_frontend_t* h);
+
+/* ------------------------------------------------------------------ ingest (step before the path) ---
+ * Replaces the numeric part of `librosa.load(path, sr=16000, mono=True)` (reference: asr_core.py:156,
+ * api/file_asr.py:271-275): decoded PCM frames -> float32 -> mean over channels -> rational resampling to 16 kHz with
+ * librosa's res_type="polyphase" (= scipy.signal.resample_poly), written into a zero-padded buffer that is the
+ * [n_chunks, 480000] input of ttasr_frontend_run.  File decoding stays with the caller.
+ * up/down: target_sr / orig_sr reduced by their gcd (1/3 for 48 kHz, 160/441 for 44.1 kHz, 1/1 = convert only).
+ * taps: host, [n_taps] fp32 = resample_poly's prototype filter firwin(2*10*max(up,down)+1, 1/max(up,down),
+ *       window=("kaiser", 5.0)) * up; ignored for 1/1. */
+TTASR_API int ttasr_ingest_create(int up, int down, const float* taps, int n_taps, ttasr_ingest_t** out);
+/* ceil(n_in * up / down), the length librosa.resample / resample_poly return */
+TTASR_API int ttasr_ingest_out_len(const ttasr_ingest_t* h, int64_t n_in, int64_t* n_out);
+/* pcm_dev: [n_in, channels] interleaved frames (TTASR_PCM_I16 scaled by 1/32768, or TTASR_PCM_F32), channels 1..8.
+ * out_dev: fp32 [out_capacity], out_capacity >= out_len(n_in); samples past the resampled signal are zero-filled. */
+TTASR_API int ttasr_ingest_run(const ttasr_ingest_t* h, const void* pcm_dev, int pcm_dtype, int channels, int64_t n_in,
+                     float* out_dev, int64_t out_capacity, void* stream);
+TTASR_API void ttasr_ingest_destroy(ttasr_ingest_t* h);
 
 /* ------------------------------------------------------------------ Whisper encoder --------------------------*/
 typedef struct {

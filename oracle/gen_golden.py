@@ -8,6 +8,7 @@ Inputs are regenerated from seeds (oracle.frontend.synth_*), weights from oracle
 from __future__ import annotations
 
 import os
+import sys
 
 import numpy as np
 import torch
@@ -76,5 +77,33 @@ def main() -> None:
         print(f, os.path.getsize(os.path.join(GOLDEN_DIR, f)), "bytes")
 
 
+def gen_ingest():
+    """tests/golden/ingest_scipy.npz: scipy.signal.resample_poly (the function librosa's res_type="polyphase" calls)
+    run directly on deterministic frames, independent of oracle/ingest.py's own wrapper."""
+    import math
+
+    import scipy.signal
+
+    from oracle import ingest as OI
+
+    out = {}
+    for sr, ch, dt in ((48000, 2, np.int16), (44100, 2, np.int16), (44100, 1, np.float32), (8000, 1, np.int16)):
+        frames = OI.synth_frames(sr, 0.25, ch, dt, seed=5)
+        x = frames.astype(np.float32) / np.float32(32768.0) if dt == np.int16 else frames.astype(np.float32)
+        if ch > 1:
+            x = x.mean(axis=1, dtype=np.float32)
+        g = math.gcd(sr, 16000)
+        y = scipy.signal.resample_poly(x.astype(np.float32), 16000 // g, sr // g)
+        n = int(math.ceil(len(x) * 16000 / sr))
+        out[f"{sr}_{ch}_{np.dtype(dt).name}"] = np.asarray(y[:n], dtype=np.float32)
+    path = os.path.join(GOLDEN_DIR, "ingest_scipy.npz")
+    np.savez_compressed(path, **out)
+    print("ingest_scipy.npz", os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
-    main()
+    if "--ingest-only" in sys.argv:
+        gen_ingest()
+    else:
+        main()
+        gen_ingest()

@@ -14,6 +14,7 @@
 #include "fft400.cuh"
 #include "frontend_logmel.h"
 #include "gemm_sm100.h"
+#include "ingest_resample.h"
 #include "layernorm.h"
 #include "ptx_sm100.cuh"
 
@@ -209,6 +210,86 @@ void ttasr_frontend_destroy(ttasr_frontend_t* h) {
   cudaFree(h->table_mem);
   cudaFree(h->chunk_max);
   cudaFree(h->tile_min);
+  delete h;
+}
+
+}  // extern "C"
+
+// =================================================================================================== ingest
+struct ttasr_ingest {
+  IngestPlan plan;
+  float* table = nullptr;
+};
+
+extern "C" {
+
+int ttasr_ingest_create(int up, int down, const float* taps, int n_taps, ttasr_ingest_t** out) {
+  if (!out) return fail(TTASR_E_ARG, "ingest_create: null argument");
+  *out = nullptr;
+  if (up < 1 || down < 1 || up > 4096 || down > 4096) return fail(TTASR_E_ARG, "ingest_create: up/down must be in [1, 4096] (got %d, %d)", up, down);
+  if (std::__gcd(up, down) != 1) return fail(TTASR_E_ARG, "ingest_create: up/down must be reduced by their gcd (got %d/%d)", up, down);
+  const bool identity = (up == 1 && down == 1);
+  if (!identity && (!taps || n_taps < 1 || (n_taps & 1) == 0 || n_taps > (1 << 20)))
+    return fail(TTASR_E_ARG, "ingest_create: the prototype filter must have an odd number of taps (got %d)", n_taps);
+  int device = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  int rc = check_arch(device, nullptr);
+  if (rc != TTASR_OK) return rc;
+  auto* h = new ttasr_ingest();
+  h->plan.up = up;
+  h->plan.down = down;
+  if (!identity) {
+    // scipy.signal.resample_poly: centre the filter on the output grid
+    const int half_len = (n_taps - 1) / 2;
+    h->plan.n_taps = n_taps;
+    h->plan.n_pre_pad = down - half_len % down;
+    h->plan.n_pre_remove = (half_len + h->plan.n_pre_pad) / down;
+    h->plan.taps_per_phase = (n_taps + up - 1) / up;
+    std::vector<float> tab(static_cast<size_t>(up) * h->plan.taps_per_phase, 0.f);
+    for (int j = 0; j < n_taps; ++j) tab[static_cast<size_t>(j % up) * h->plan.taps_per_phase + j / up] = taps[j];
+    cudaError_t e = cudaMalloc(&h->table, tab.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(h->table, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+      cudaFree(h->table);
+      delete h;
+      return fail(TTASR_E_CUDA, "ingest_create: %s", cudaGetErrorString(e));
+    }
+    h->plan.phase_taps = h->table;
+  }
+  *out = h;
+  return TTASR_OK;
+}
+
+int ttasr_ingest_out_len(const ttasr_ingest_t* h, int64_t n_in, int64_t* n_out) {
+  if (!h || !n_out) return fail(TTASR_E_ARG, "ingest_out_len: null argument");
+  if (n_in < 0) return fail(TTASR_E_SHAPE, "ingest_out_len: negative length");
+  const int64_t x = n_in * h->plan.up;
+  *n_out = x / h->plan.down + (x % h->plan.down != 0);
+  return TTASR_OK;
+}
+
+int ttasr_ingest_run(const ttasr_ingest_t* h, const void* pcm_dev, int pcm_dtype, int channels, int64_t n_in,
+                     float* out_dev, int64_t out_capacity, void* stream) {
+  if (!h) return fail(TTASR_E_ARG, "ingest_run: null handle");
+  if (pcm_dtype != TTASR_PCM_F32 && pcm_dtype != TTASR_PCM_I16) return fail(TTASR_E_ARG, "ingest_run: bad pcm_dtype %d", pcm_dtype);
+  if (channels < 1 || channels > 8) return fail(TTASR_E_SHAPE, "ingest_run: channels must be in [1, 8] (got %d)", channels);
+  if (n_in < 0 || out_capacity < 0) return fail(TTASR_E_SHAPE, "ingest_run: negative length");
+  int64_t n_out = 0;
+  ttasr_ingest_out_len(h, n_in, &n_out);
+  if (out_capacity < n_out) return fail(TTASR_E_SHAPE, "ingest_run: out_capacity %lld < %lld resampled samples", (long long)out_capacity, (long long)n_out);
+  if (out_capacity == 0) return TTASR_OK;
+  if (!out_dev || (n_in > 0 && !pcm_dev)) return fail(TTASR_E_ARG, "ingest_run: null buffer");
+  const size_t esz = pcm_dtype == TTASR_PCM_I16 ? 2 : 4;
+  if (channels == 2 && (reinterpret_cast<uintptr_t>(pcm_dev) % (2 * esz)) != 0) return fail(TTASR_E_ARG, "ingest_run: stereo input must be aligned to one frame");
+  cudaError_t e = launch_ingest(h->plan, pcm_dev, pcm_dtype == TTASR_PCM_I16, channels, n_in, out_dev, n_out, out_capacity,
+                                static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(TTASR_E_CUDA, "ingest_run: launch failed: %s", cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+void ttasr_ingest_destroy(ttasr_ingest_t* h) {
+  if (!h) return;
+  cudaFree(h->table);
   delete h;
 }
 

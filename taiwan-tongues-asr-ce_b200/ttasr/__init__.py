@@ -6,9 +6,10 @@ or PyTorch fallback: importing is cheap, but any compute call without the built 
 from ._lib import TtasrError, abi_version, library_path  # noqa: F401
 from .encoder import B200WhisperEncoder, EncoderConfig  # noqa: F401
 from .feature_extractor import B200WhisperFeatureExtractor  # noqa: F401
+from .ingest import B200AudioIngest, resample_poly_filter  # noqa: F401
 from .pipeline import B200LogMelEncoder  # noqa: F401
 
 __all__ = [
-    "B200WhisperFeatureExtractor", "B200WhisperEncoder", "EncoderConfig", "B200LogMelEncoder",
+    "B200WhisperFeatureExtractor", "B200WhisperEncoder", "EncoderConfig", "B200LogMelEncoder", "B200AudioIngest", "resample_poly_filter",
     "TtasrError", "abi_version", "library_path",
 ]

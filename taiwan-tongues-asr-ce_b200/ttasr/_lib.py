@@ -50,6 +50,11 @@ PROTOTYPES = {
                                      C.c_void_p, C.c_int, C.c_void_p]),
     "ttasr_frontend_max_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "ttasr_frontend_destroy": (None, [C.c_void_p]),
+    "ttasr_ingest_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "ttasr_ingest_out_len": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "ttasr_ingest_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
+                                   C.c_void_p]),
+    "ttasr_ingest_destroy": (None, [C.c_void_p]),
     "ttasr_encoder_create": (C.c_int, [C.POINTER(EncoderCfg), C.POINTER(Weights), C.POINTER(C.c_void_p)]),
     "ttasr_encoder_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]),
     "ttasr_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_size_t,
