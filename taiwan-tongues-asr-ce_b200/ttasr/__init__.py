@@ -4,6 +4,7 @@ Host side of the C ABI in include/ttasr_abi.h (lib/libttasr_b200.so, hand-writte
 or PyTorch fallback: importing is cheap, but any compute call without the built library or without a B200 raises.
 """
 from ._lib import TtasrError, abi_version, library_path  # noqa: F401
+from . import decode_handoff  # noqa: F401
 from .encoder import B200WhisperEncoder, EncoderConfig  # noqa: F401
 from .feature_extractor import B200WhisperFeatureExtractor  # noqa: F401
 from .ingest import B200AudioIngest, resample_poly_filter  # noqa: F401
