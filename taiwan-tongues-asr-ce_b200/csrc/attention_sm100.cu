@@ -32,10 +32,6 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef TTASR_ATTN_PRETOKEN
 #define TTASR_ATTN_PRETOKEN 1
 #endif
-#ifndef TTASR_ATTN_EMUL
-#define TTASR_ATTN_EMUL 0
-#endif
-constexpr bool kEmulatePreToken = TTASR_ATTN_EMUL != 0;  // pre-token quarter: exponentials on the FMA pipe
 constexpr int kPreTokenChunks = TTASR_ATTN_PRETOKEN;  // quarters of the exp sweep done outside the token
 constexpr float kRescaleThreshold = 32.0f;  // log2 units: P stays <= 2^32 (bf16 range 2^127, O and l are fp32)
 
@@ -117,28 +113,47 @@ __device__ __forceinline__ void mask_tail(uint32_t (&v)[32], int col0, int valid
 
 // p_i = 2^(s_i*log2e - m_used), written back over the scores; the row sum and the bf16 packing (sum_pack) of a chunk
 // are issued after the exponentials of the next chunk.
+#ifndef TTASR_ATTN_F32X2
+#define TTASR_ATTN_F32X2 1
+#endif
 __device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], float m_used) {
+#if TTASR_ATTN_F32X2
+  // packed FFMA2: one issue slot scales and shifts two scores (the sweep shares its scheduler with the MMA / TMA warps)
+  const float neg_m = -m_used;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    asm("{ .reg .b64 t, u, w;\n\t"
+        "mov.b64 t, {%0, %1};\n\t"
+        "mov.b64 u, {%2, %2};\n\t"
+        "mov.b64 w, {%3, %3};\n\t"
+        "fma.rn.f32x2 t, t, u, w;\n\t"
+        "mov.b64 {%0, %1}, t; }"
+        : "+r"(v[i]), "+r"(v[i + 1])
+        : "r"(__float_as_uint(kLog2e)), "r"(__float_as_uint(neg_m)));
+    v[i] = __float_as_uint(ex2(__uint_as_float(v[i])));
+    v[i + 1] = __float_as_uint(ex2(__uint_as_float(v[i + 1])));
+  }
+#else
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2(fmaf(__uint_as_float(v[i]), kLog2e, -m_used)));
-}
-// 2^x on the FMA/ALU pipes (no MUFU): x = n + f with f in [-0.5, 0.5] (round-to-nearest via the 1.5*2^23 trick), cubic
-// for 2^f (max rel err 7.7e-5, far inside P's bf16 rounding), n added into the exponent field.  x is clamped at -126
-// (masked keys: -inf -> ~1e-38 ~ 0).  Used for the part of the sweep that runs beside the other warpgroup's
-// exclusive sweep, so that it does not compete for the exp pipe.
-__device__ __forceinline__ float ex2_fma(float x) {
-  x = fmaxf(x, -126.0f);
-  const float xr = x + 12582912.0f;
-  const float f = x - (xr - 12582912.0f);
-  float p = fmaf(0.055088683807511155f, f, 0.2426040514594791f);
-  p = fmaf(p, f, 0.6932762416819607f);
-  p = fmaf(p, f, 0.9999289403695112f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
-}
-__device__ __forceinline__ void exp_inplace_fma(uint32_t (&v)[32], float m_used) {
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2_fma(fmaf(__uint_as_float(v[i]), kLog2e, -m_used)));
+#endif
 }
 __device__ __forceinline__ float sum_pack(const uint32_t (&v)[32], uint32_t (&pk)[16]) {
+#if TTASR_ATTN_F32X2
+  uint32_t s0 = 0u, s1 = 0u;  // two packed fp32 partial sums
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    asm("{ .reg .b64 t, u;\n\t"
+        "mov.b64 t, {%0, %1};\n\t"
+        "mov.b64 u, {%2, %3};\n\t"
+        "add.rn.f32x2 t, t, u;\n\t"
+        "mov.b64 {%0, %1}, t; }"
+        : "+r"(s0), "+r"(s1)
+        : "r"(v[2 * i]), "r"(v[2 * i + 1]));
+    pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+  }
+  return __uint_as_float(s0) + __uint_as_float(s1);
+#else
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
@@ -148,6 +163,7 @@ __device__ __forceinline__ float sum_pack(const uint32_t (&v)[32], uint32_t (&pk
     pk[i] = pack_bf16x2(p0, p1);
   }
   return sum0 + sum1;
+#endif
 }
 
 __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid_constant__ AttnParams p) {
@@ -429,8 +445,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         };
         auto tok_acquire = [&]() { tr(15); asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory"); tr(16); };
         if (kPreTokenChunks == 0) tok_acquire();
-        if (kPreTokenChunks >= 1 && kEmulatePreToken) exp_inplace_fma(v0, m_used);
-        else stage_a(v0, 0);
+        stage_a(v0, 0);
         if (kPreTokenChunks == 1) tok_acquire();
         stage_a(v1, 1);
         stage_b(v0, 0);
