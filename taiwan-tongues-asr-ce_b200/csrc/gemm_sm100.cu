@@ -72,6 +72,9 @@ __device__ __forceinline__ void sts128u(uint32_t addr, uint32_t a, uint32_t b, u
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+#ifndef TTASR_GELU_F32X2
+#define TTASR_GELU_F32X2 1
+#endif
 template <int ACT>
 __device__ __forceinline__ float apply_act(float x) {
   if constexpr (ACT == 1) return gelu_erf(x);
@@ -291,14 +294,27 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
             const float4 bv = __ldg(bias4 + c);
             const uint32_t addr = slab + row_off + ((c ^ swz) << 4);
             float4 v;
-            v.x = apply_act<ACT>(__uint_as_float(acc[4 * c + 0]) + bv.x);
-            v.y = apply_act<ACT>(__uint_as_float(acc[4 * c + 1]) + bv.y);
-            v.z = apply_act<ACT>(__uint_as_float(acc[4 * c + 2]) + bv.z);
-            v.w = apply_act<ACT>(__uint_as_float(acc[4 * c + 3]) + bv.w);
-            if (HAS_ADD) {
-              float4 a;
-              lds128(addr, a);
-              v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+            if constexpr (ACT == 0 && TTASR_GELU_F32X2) {  // packed adds: acc + bias (+ addend), two lanes per issue slot
+              f32x2_t lo = add2(pack2(__uint_as_float(acc[4 * c + 0]), __uint_as_float(acc[4 * c + 1])), pack2(bv.x, bv.y));
+              f32x2_t hi = add2(pack2(__uint_as_float(acc[4 * c + 2]), __uint_as_float(acc[4 * c + 3])), pack2(bv.z, bv.w));
+              if (HAS_ADD) {
+                float4 a;
+                lds128(addr, a);
+                lo = add2(lo, pack2(a.x, a.y));
+                hi = add2(hi, pack2(a.z, a.w));
+              }
+              unpack2(lo, v.x, v.y);
+              unpack2(hi, v.z, v.w);
+            } else {
+              v.x = apply_act<ACT>(__uint_as_float(acc[4 * c + 0]) + bv.x);
+              v.y = apply_act<ACT>(__uint_as_float(acc[4 * c + 1]) + bv.y);
+              v.z = apply_act<ACT>(__uint_as_float(acc[4 * c + 2]) + bv.z);
+              v.w = apply_act<ACT>(__uint_as_float(acc[4 * c + 3]) + bv.w);
+              if (HAS_ADD) {
+                float4 a;
+                lds128(addr, a);
+                v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+              }
             }
             sts128(addr, v);
           }
@@ -318,6 +334,24 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
           for (int c = 0; c < 8; ++c) {  // 16-byte chunk = 8 bf16 columns
             const uint32_t* a = (c < 4) ? &acc0[8 * c] : &acc1[8 * (c - 4)];
             const float4 b0 = __ldg(bias4 + 2 * c), b1 = __ldg(bias4 + 2 * c + 1);
+            if constexpr (ACT == 1 && TTASR_GELU_F32X2) {
+              const uint32_t o0 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack2(b0.x, b0.y)));
+              const uint32_t o1 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(a[2]), __uint_as_float(a[3])), pack2(b0.z, b0.w)));
+              const uint32_t o2 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack2(b1.x, b1.y)));
+              const uint32_t o3 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(a[6]), __uint_as_float(a[7])), pack2(b1.z, b1.w)));
+              sts128u(slab + row_off + ((c ^ swz) << 4), o0, o1, o2, o3);
+              continue;
+            }
+            if constexpr (ACT == 0 && TTASR_GELU_F32X2) {
+              float r[8];
+              unpack2(add2(pack2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack2(b0.x, b0.y)), r[0], r[1]);
+              unpack2(add2(pack2(__uint_as_float(a[2]), __uint_as_float(a[3])), pack2(b0.z, b0.w)), r[2], r[3]);
+              unpack2(add2(pack2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack2(b1.x, b1.y)), r[4], r[5]);
+              unpack2(add2(pack2(__uint_as_float(a[6]), __uint_as_float(a[7])), pack2(b1.z, b1.w)), r[6], r[7]);
+              sts128u(slab + row_off + ((c ^ swz) << 4), pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]),
+                      pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+              continue;
+            }
             const float v0 = apply_act<ACT>(__uint_as_float(a[0]) + b0.x);
             const float v1 = apply_act<ACT>(__uint_as_float(a[1]) + b0.y);
             const float v2 = apply_act<ACT>(__uint_as_float(a[2]) + b0.z);

@@ -336,4 +336,50 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-ax, h, fmaxf(x, 0.0f));
 }
 
+
+// ---- packed fp32 pairs (FFMA2 / FADD2 / FMUL2 on sm_100): one issue slot per two lanes of work
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// gelu_erf on two values at once (same arithmetic as gelu_erf, FMA-pipe work issued as packed pairs); returns bf16x2
+__device__ __forceinline__ uint32_t gelu_erf_bf16x2(f32x2_t x) {
+  float x0, x1;
+  unpack2(x, x0, x1);
+  const f32x2_t nax = pack2(-fabsf(x0), -fabsf(x1));
+  float d0, d1, q0, q1;
+  unpack2(fma2(pack2(-0.23164189f, -0.23164189f), nax, pack2(1.0f, 1.0f)), d0, d1);
+  unpack2(mul2(mul2(x, x), pack2(-0.72134752044448170f, -0.72134752044448170f)), q0, q1);
+  const f32x2_t t = pack2(rcp_approx(d0), rcp_approx(d1));
+  const f32x2_t e = pack2(ex2_approx(q0), ex2_approx(q1));
+  f32x2_t p = fma2(pack2(0.5307027145f, 0.5307027145f), t, pack2(-0.7265760135f, -0.7265760135f));
+  p = fma2(p, t, pack2(0.7107068705f, 0.7107068705f));
+  p = fma2(p, t, pack2(-0.142248368f, -0.142248368f));
+  p = fma2(p, t, pack2(0.127414796f, 0.127414796f));
+  const f32x2_t h = mul2(mul2(p, t), e);
+  float r0, r1;
+  unpack2(fma2(nax, h, pack2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), r0, r1);
+  return pack_bf16x2(r0, r1);
+}
+
 }  // namespace ttasr
