@@ -24,8 +24,8 @@ class B200LogMelEncoder:
 
     @property
     def launches_per_call(self) -> int:
-        # fill + frames + finalize (front end) and the encoder's sequence minus its unused fp32->bf16 transpose
-        return 3 + self.encoder.launches_per_forward - 1
+        # frames + clamp kernels (front end) and the encoder's sequence minus its unused fp32->bf16 transpose
+        return 2 + self.encoder.launches_per_forward - 1
 
     def encode_device(self, pcm, n_valid=None, out_dtype=None):
         """pcm: CUDA [B, n_samples] float32 / int16 -> [B, 1500, d] CUDA."""
@@ -49,17 +49,20 @@ class B200LogMelEncoder:
             return out_host
         return hidden
 
-    def stream_host(self, batches, outs):
+    def stream_host(self, batches, outs=None, consume=None):
         """Pipelined host-to-host run over a sequence of batches: while batch k is in the kernels, batch k+1's PCM is
         copied in and batch k-1's hidden states are copied out (three streams, double-buffered device staging).
 
         batches: sequence of pinned CPU tensors [B, n_samples] (float32 or int16, same shape/dtype);
-        outs:    sequence of pinned CPU tensors [B, 1500, d] bf16 receiving the hidden states.
+        outs:    sequence of pinned CPU tensors [B, 1500, d] bf16 receiving the hidden states, or None to leave the
+                 results on the device (then `consume(k, hidden)` — if given — is called with each batch's CUDA
+                 tensor, stream-ordered on the current stream, before its buffer is reused two batches later).
         Returns when everything has been enqueued; synchronise the current stream (or the device) to wait."""
         import torch
 
-        batches, outs = list(batches), list(outs)
-        if len(batches) != len(outs):
+        batches = list(batches)
+        outs = list(outs) if outs is not None else None
+        if outs is not None and len(batches) != len(outs):
             raise _lib.TtasrError(-2, "stream_host needs one output buffer per batch")
         if not batches:
             return
@@ -84,11 +87,15 @@ class B200LogMelEncoder:
                 buf.copy_(pcm, non_blocking=True)
                 in_ready[k].record(h2d)
             main.wait_event(in_ready[k])
-            if k >= 2:
+            if k >= 2 and outs is not None:
                 main.wait_event(out_ready[k - 2])  # hidden[k & 1] has been copied out before it is overwritten
             _, tm = self.feature_extractor.extract(buf, return_time_major=True)
             in_free[k].record(main)
             hidden[k & 1] = self.encoder.encode(tm, time_major_ld=tm.shape[2])
+            if consume is not None:
+                consume(k, hidden[k & 1])
+            if outs is None:
+                continue
             done = torch.cuda.Event()
             done.record(main)
             with torch.cuda.stream(d2h):
