@@ -45,10 +45,9 @@ struct __align__(16) FrontSmem {
   float ti[kGroups * kTStride];    // (im);                 Z (im);       power of the odd frame
   float2 tw[kNfft];                // W400^(n2*k1) at [k1*20 + n2]
   float win[kNfft];
-  float melw[kMaxMelNnz];
-  int mel_lo[kMaxMels];
-  int mel_cnt[kMaxMels];
-  int mel_off[kMaxMels];
+  int4 mel_ops[kMaxMelOps];
+  int mel_op_off[kMelWarps + 1];
+  int mel_m0[kMelWarps + 1];
   float wmin[kThreads / 32];
   unsigned long long bar;
 };
@@ -93,11 +92,10 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
     s.tw[i] = tables.twiddle[i];
     s.win[i] = tables.window[i];
   }
-  for (int i = tid; i < kMaxMelNnz; i += kThreads) s.melw[i] = tables.mel_w[i];
-  for (int i = tid; i < kMaxMels; i += kThreads) {
-    s.mel_lo[i] = tables.mel_lo[i];
-    s.mel_cnt[i] = tables.mel_cnt[i];
-    s.mel_off[i] = tables.mel_off[i];
+  for (int i = tid; i < kMaxMelOps; i += kThreads) s.mel_ops[i] = tables.mel_ops[i];
+  if (tid <= kMelWarps) {
+    s.mel_op_off[tid] = tables.mel_op_off[tid];
+    s.mel_m0[tid] = tables.mel_m0[tid];
   }
   const uint32_t bar = smem_u32(&s.bar);
   if (tid == 0) {
@@ -248,26 +246,37 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         }
       }
       __syncthreads();
-      // ---------------- mel gather + log10 + store: warp w owns filters w, w + 10, ...; lane = frame within the tile
+      // ---------------- mel projection + log + store.  lane = frame within the tile; warp w owns a contiguous range of
+      // filters and walks its frequency bins once with two accumulators (a bin feeds <= 2 adjacent triangles): the
+      // program (bin, weight for the current filter, weight for the next one, filters completed) is built on the host.
       {
-        const int lane = tid & 31;
+        const int lane = tid & 31, wrp = tid >> 5;
         const bool live = (t0 + lane) < n_frames;
-        float* out_col = raw + static_cast<long long>(b) * n_mels * n_frames + t0 + lane;
-        __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2);  // ti is idle by now
-        for (int m = tid >> 5; m < n_mels; m += kThreads / 32) {
-          const float* pwm = &s.tr[s.mel_lo[m] * kPwPitch + lane];
-          const float* w = &s.melw[s.mel_off[m]];
-          const int cnt = s.mel_cnt[m];
-          float acc = 0.f;
-          for (int j = 0; j < cnt; ++j) acc = fmaf(w[j], pwm[j * kPwPitch], acc);
-          // (log10 + 4) / 4 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate); the floor is returned exactly
-          const float v = acc > kMelFloor ? fmaf(__log2f(acc), kLog2ToY, 1.0f) : kYFloor;
-          if (live) {
-            out_col[static_cast<long long>(m) * n_frames] = v;
-            tmax = fmaxf(tmax, v);
-            tmin = fminf(tmin, v);
+        int m = s.mel_m0[wrp];
+        float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
+        __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
+        const float* pw = &s.tr[lane];
+        float acc_a = 0.f, acc_b = 0.f;
+        const int op_end = s.mel_op_off[wrp + 1];
+        for (int i = s.mel_op_off[wrp]; i < op_end; ++i) {
+          const int4 op = s.mel_ops[i];
+          const float p = pw[op.x * kPwPitch];
+          acc_a = fmaf(__int_as_float(op.y), p, acc_a);
+          acc_b = fmaf(__int_as_float(op.z), p, acc_b);
+          for (int e = 0; e < op.w; ++e) {
+            // (log10 + 4) / 4 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate); the floor is returned exactly
+            const float v = acc_a > kMelFloor ? fmaf(__log2f(acc_a), kLog2ToY, 1.0f) : kYFloor;
+            if (live) {
+              *out_ptr = v;
+              tmax = fmaxf(tmax, v);
+              tmin = fminf(tmin, v);
+            }
+            if (tmajor) *stg = __float2bfloat16_rn(v);
+            acc_a = acc_b;
+            acc_b = 0.f;
+            out_ptr += n_frames;
+            ++stg;
           }
-          if (tmajor) stg[m] = __float2bfloat16_rn(v);
         }
       }
       __syncthreads();  // power spectra consumed before the next tile's pass 1 overwrites the buffer; staging complete

@@ -7,16 +7,16 @@
 namespace ttasr {
 
 constexpr int kMaxMels = 128;
-constexpr int kMaxMelNnz = 512;  // sum over filters of (last_nonzero_bin - first_nonzero_bin + 1); 394 at 128 mels
+constexpr int kMelWarps = 10;    // warps of the frames kernel (320 threads); each owns a contiguous range of filters
+constexpr int kMaxMelOps = 512;  // entries of the streaming mel program (one per frequency bin walked, per warp)
 
 // device-resident constant tables owned by the front-end handle
 struct FrontTables {
   const float2* twiddle;  // [400]  W400^(n2*k1) = (cos, -sin)(2 pi n2 k1 / 400) at [k1*20 + n2]
   const float* window;    // [400]  periodic Hann
-  const float* mel_w;     // [kMaxMelNnz] filter weights, filter m occupies [mel_off[m], mel_off[m]+mel_cnt[m])
-  const int* mel_lo;      // [kMaxMels] first frequency bin of filter m
-  const int* mel_cnt;     // [kMaxMels]
-  const int* mel_off;     // [kMaxMels]
+  const int4* mel_ops;    // [kMaxMelOps] {bin, weight of filter m_cur, weight of filter m_cur + 1, filters completed}
+  const int* mel_op_off;  // [kMelWarps + 1] warp w runs ops [mel_op_off[w], mel_op_off[w + 1])
+  const int* mel_m0;      // [kMelWarps + 1] warp w owns filters [mel_m0[w], mel_m0[w + 1])
 };
 
 size_t frontend_smem_bytes();

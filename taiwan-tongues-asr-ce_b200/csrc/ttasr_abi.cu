@@ -126,32 +126,88 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
       const double ang = -2.0 * M_PI * static_cast<double>(n2 * k1) / kNfft;
       tw[k1 * kRadix + n2] = make_float2(static_cast<float>(cos(ang)), static_cast<float>(sin(ang)));
     }
-  std::vector<float> melw(kMaxMelNnz, 0.f);
-  std::vector<int> lo(kMaxMels, 0), cnt(kMaxMels, 0), off(kMaxMels, 0);
-  int used = 0;
-  for (int m = 0; m < n_mels; ++m) {
-    int first = -1, last = -1;
+  // ---- mel projection as a streaming program per warp (frontend_logmel.cu, mel pass): a frequency bin of a
+  // triangular bank feeds at most two ADJACENT filters, so a warp that owns filters [m0, m1) walks its bins once in
+  // ascending order with two accumulators (filter m_cur and m_cur + 1) and "emits" a filter when its last bin is
+  // behind it.  op = {bin, weight for m_cur, weight for m_cur + 1, filters to emit after this bin}.
+  std::vector<int> first(n_mels, -1), last(n_mels, -1);
+  for (int m = 0; m < n_mels; ++m)
     for (int k = 0; k < kNfreq; ++k)
       if (mel_filters[k * n_mels + m] != 0.f) {
-        if (first < 0) first = k;
-        last = k;
+        if (first[m] < 0) first[m] = k;
+        last[m] = k;
       }
-    if (first < 0) continue;  // all-zero filter: cnt 0 -> power 0 -> floor
-    const int c = last - first + 1;
-    if (used + c > kMaxMelNnz) return fail(TTASR_E_SHAPE, "frontend_create: mel filter bank too dense (> %d band entries)", kMaxMelNnz);
-    lo[m] = first;
-    cnt[m] = c;
-    off[m] = used;
-    for (int j = 0; j < c; ++j) melw[used + j] = mel_filters[(first + j) * n_mels + m];
-    used += c;
+  // contiguous filter ranges of roughly equal cost (bins walked + ~2 bin-equivalents per emitted filter)
+  std::vector<int> warp_m0(kMelWarps + 1, n_mels);
+  {
+    std::vector<double> cost(n_mels);
+    double total = 0;
+    for (int m = 0; m < n_mels; ++m) {
+      const int prev_last = (m > 0 && last[m - 1] >= 0) ? last[m - 1] : -1;
+      cost[m] = 2.0 + (last[m] >= 0 ? std::max(0, last[m] - std::max(prev_last, first[m] - 1)) : 0);
+      total += cost[m];
+    }
+    double acc = 0;
+    int w = 0;
+    warp_m0[0] = 0;
+    for (int m = 0; m < n_mels; ++m) {
+      if (w + 1 < kMelWarps && acc >= total * (w + 1) / kMelWarps) warp_m0[++w] = m;
+      acc += cost[m];
+    }
+    for (int i = w + 1; i <= kMelWarps; ++i) warp_m0[i] = n_mels;
   }
+  std::vector<int4> ops;
+  std::vector<int> op_off(kMelWarps + 1, 0);
+  auto weight = [&](int k, int m) { return mel_filters[k * n_mels + m]; };
+  for (int w = 0; w < kMelWarps; ++w) {
+    op_off[w] = static_cast<int>(ops.size());
+    const int m0 = warp_m0[w], m1 = warp_m0[w + 1];
+    if (m0 >= m1) continue;
+    int k_begin = kNfreq, k_end = -1;
+    for (int m = m0; m < m1; ++m)
+      if (first[m] >= 0) {
+        k_begin = std::min(k_begin, first[m]);
+        k_end = std::max(k_end, last[m]);
+      }
+    int m_cur = m0;
+    auto emit_into_last = [&](int n) {  // n more filters are complete
+      if (n <= 0) return;
+      if (static_cast<int>(ops.size()) == op_off[w]) ops.push_back(make_int4(0, 0, 0, 0));  // nothing walked yet
+      ops.back().w += n;
+      m_cur += n;
+    };
+    for (int k = k_begin; k <= k_end && m_cur < m1; ++k) {
+      int done = 0;  // filters (from m_cur on) whose last non-zero bin lies before k
+      while (m_cur + done < m1 && last[m_cur + done] < k) ++done;
+      emit_into_last(done);
+      if (m_cur >= m1) break;
+      for (int m = m0; m < m1; ++m)
+        if (weight(k, m) != 0.f && (m < m_cur || m > m_cur + 1)) {
+          return fail(TTASR_E_SHAPE, "frontend_create: mel filter bank is not a bank of overlapping triangles "
+                                     "(frequency bin %d feeds filter %d besides %d and %d)", k, m, m_cur, m_cur + 1);
+        }
+      const float wa = weight(k, m_cur);
+      const float wb = (m_cur + 1 < m1) ? weight(k, m_cur + 1) : 0.f;
+      int4 op;
+      op.x = k;
+      memcpy(&op.y, &wa, 4);
+      memcpy(&op.z, &wb, 4);
+      op.w = 0;
+      ops.push_back(op);
+    }
+    emit_into_last(m1 - m_cur);
+  }
+  op_off[kMelWarps] = static_cast<int>(ops.size());
+  if (static_cast<int>(ops.size()) > kMaxMelOps)
+    return fail(TTASR_E_SHAPE, "frontend_create: mel program too long (%d > %d ops)", static_cast<int>(ops.size()), kMaxMelOps);
+  ops.resize(kMaxMelOps, make_int4(0, 0, 0, 0));
 
   ttasr_frontend* h = new ttasr_frontend();
   h->device = device;
   h->num_sms = sms;
   h->n_mels = n_mels;
   h->n_samples = n_samples;
-  const size_t bytes = sizeof(float2) * kNfft + sizeof(float) * kNfft + sizeof(float) * kMaxMelNnz + 3 * sizeof(int) * kMaxMels;
+  const size_t bytes = sizeof(float2) * kNfft + sizeof(int4) * kMaxMelOps + sizeof(float) * kNfft + 2 * sizeof(int) * (kMelWarps + 1);
   cudaError_t e = cudaMalloc(&h->table_mem, bytes);
   if (e != cudaSuccess) { delete h; return fail(TTASR_E_NOMEM, "frontend_create: cudaMalloc tables: %s", cudaGetErrorString(e)); }
   char* pdev = static_cast<char*>(h->table_mem);
@@ -162,11 +218,10 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
     return dst;
   };
   h->tables.twiddle = static_cast<const float2*>(put(tw.data(), sizeof(float2) * kNfft));
+  h->tables.mel_ops = static_cast<const int4*>(put(ops.data(), sizeof(int4) * kMaxMelOps));   // 16-byte aligned
   h->tables.window = static_cast<const float*>(put(window, sizeof(float) * kNfft));
-  h->tables.mel_w = static_cast<const float*>(put(melw.data(), sizeof(float) * kMaxMelNnz));
-  h->tables.mel_lo = static_cast<const int*>(put(lo.data(), sizeof(int) * kMaxMels));
-  h->tables.mel_cnt = static_cast<const int*>(put(cnt.data(), sizeof(int) * kMaxMels));
-  h->tables.mel_off = static_cast<const int*>(put(off.data(), sizeof(int) * kMaxMels));
+  h->tables.mel_op_off = static_cast<const int*>(put(op_off.data(), sizeof(int) * (kMelWarps + 1)));
+  h->tables.mel_m0 = static_cast<const int*>(put(warp_m0.data(), sizeof(int) * (kMelWarps + 1)));
   h->max_batch = 1 << 14;
   e = cudaMalloc(&h->chunk_max, sizeof(unsigned) * h->max_batch);
   if (e == cudaSuccess) e = cudaMalloc(&h->tile_min, sizeof(float) * h->max_batch * frontend_tiles(n_samples));
