@@ -48,7 +48,7 @@ struct __align__(16) FrontSmem {
   int4 mel_ops[kMaxMelOps];
   int mel_op_off[kMelWarps + 1];
   int mel_m0[kMelWarps + 1];
-  float wmin[kThreads / 32];
+  float wmin[2][kThreads / 32];   // per-warp tile minima, double-buffered by tile parity (see the reduction)
   unsigned long long bar;
 };
 
@@ -144,6 +144,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
   // tiles are walked with stride gridDim.x; (chunk, tile-in-chunk) advance incrementally (no 64-bit division per tile)
   const int step_b = static_cast<int>(gridDim.x) / tiles_per_chunk, step_t = static_cast<int>(gridDim.x) % tiles_per_chunk;
   uint32_t phase = 0;
+  int wbuf = 0;
   long long tile = blockIdx.x;
   int b = static_cast<int>(blockIdx.x) / tiles_per_chunk, tt = static_cast<int>(blockIdx.x) % tiles_per_chunk;
   int kind_cur = 0;
@@ -301,17 +302,20 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
       tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
       tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
     }
+    // (double-buffered: a padding tile reaches this point without any block barrier, so the other warps may already
+    // be writing the NEXT tile's minima while thread 0 still reads this tile's)
     if ((tid & 31) == 0) {
       if (tmax > -INFINITY) atomicMax(&chunk_max[b], enc_ordered(tmax));
-      s.wmin[tid >> 5] = tmin;
+      s.wmin[wbuf][tid >> 5] = tmin;
     }
     __syncthreads();
     if (tid == 0) {
-      float m = s.wmin[0];
+      float m = s.wmin[wbuf][0];
 #pragma unroll
-      for (int w = 1; w < kThreads / 32; ++w) m = fminf(m, s.wmin[w]);
+      for (int w = 1; w < kThreads / 32; ++w) m = fminf(m, s.wmin[wbuf][w]);
       tile_min[static_cast<long long>(b) * tiles_per_chunk + tt] = m;
     }
+    wbuf ^= 1;
     kind_cur = kind_next;
     b = b_next;
     tt = tt_next;

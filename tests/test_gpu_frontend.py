@@ -130,3 +130,26 @@ def test_clamp_pass_paths_f32_and_time_major(cuda_device, n_mels):
         want = torch.from_numpy(feats[i].T.copy()).to(torch.bfloat16).float().numpy()
         assert np.array_equal(tm[i, :, :n_mels], want), f"clip {i}: time-major copy differs from the fp32 features"
         assert np.all(tm[i, :, n_mels:] == 0)
+
+
+def test_padding_tiles_after_real_tiles_do_not_race(cuda_device):
+    """Regression: a CTA that walks from a real tile straight into an all-padding tile (no block barrier on that path)
+    used to overwrite the per-warp tile minima the previous tile was still reducing, so the clamp kernel took the real
+    tile for an unwritten one.  Ragged batch larger than one wave of CTAs, repeated with the allocator churned."""
+    import torch
+
+    rng = np.random.default_rng(5)
+    lens = [480000, 48000, 16000, 123457, 0, 480000, 300000]
+    rows = [(0.1 * rng.standard_normal(n)).astype(np.float32) for n in lens]
+    host = np.zeros((len(lens), max(lens)), np.float32)
+    for i, r in enumerate(rows):
+        host[i, : len(r)] = r
+    fe = _fe(80)
+    pcm = torch.from_numpy(host).to(cuda_device)
+    nv = torch.tensor(lens, dtype=torch.int32, device=cuda_device)
+    refs = [OF.log_mel(r, 80) for r in rows]
+    for it in range(6):
+        torch.empty((9, 80, 3000), device=cuda_device).fill_(float(it))
+        got = fe.extract(pcm, n_valid=nv).cpu().numpy()
+        for i, ref in enumerate(refs):
+            assert np.abs(got[i] - ref).max() <= TOL, f"iteration {it}, row {i} (len {lens[i]})"
