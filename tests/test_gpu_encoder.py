@@ -221,3 +221,39 @@ def test_forward_can_be_captured_in_a_cuda_graph(cuda_device):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(static_out, eager)
+
+
+def test_full_size_properties_large_v3_b256(cuda_device):
+    """BASELINE.json configs[2] at full size (large-v3, 256 x 30 s): the oracle cannot run here, so the path is checked
+    through size-independent properties — determinism (two runs bit-identical), batch-position invariance (a chunk's
+    hidden states do not depend on where it sits in the batch or on the batch size), finiteness, and the
+    all-padding chunk equal to the all-zero chunk."""
+    import torch
+    import bench
+    import ttasr
+
+    dev = cuda_device
+    cfg = ttasr.EncoderConfig.named("large-v3")
+    fe = ttasr.B200WhisperFeatureExtractor(feature_size=cfg.num_mel_bins)
+    enc = ttasr.B200WhisperEncoder(cfg, bench.make_gpu_weights(cfg, dev))
+    pipe = ttasr.B200LogMelEncoder(fe, enc)
+    B = 256
+    g = torch.Generator(device=dev).manual_seed(1234)
+    pcm = (0.1 * torch.randn((B, 480000), device=dev, generator=g)).clamp_(-1, 1)
+    pcm[7] = 0.0                                   # an all-zero chunk ...
+    nv = torch.full((B,), 480000, dtype=torch.int32, device=dev)
+    nv[9] = 0                                      # ... and an all-padding one
+    h1 = pipe.encode_device(pcm, n_valid=nv)
+    h2 = pipe.encode_device(pcm, n_valid=nv)
+    assert h1.shape == (B, 1500, cfg.d_model) and h1.dtype == torch.bfloat16
+    assert bool(torch.isfinite(h1.float()).all())
+    assert torch.equal(h1, h2), "two runs of the same batch differ"
+    assert torch.equal(h1[7], h1[9]), "all-zero chunk and all-padding chunk differ"
+    rows = [0, 100, 255, 7]
+    sub = pipe.encode_device(pcm[rows].contiguous(), n_valid=nv[rows].contiguous())
+    for k, r in enumerate(rows):
+        assert torch.equal(sub[k], h1[r]), f"chunk {r}: result depends on batch position / batch size"
+    # a permutation of the batch permutes the output
+    perm = torch.randperm(B, device=dev, generator=g)
+    hp = pipe.encode_device(pcm[perm].contiguous(), n_valid=nv[perm].contiguous())
+    assert torch.equal(hp, h1[perm])

@@ -153,3 +153,28 @@ def test_padding_tiles_after_real_tiles_do_not_race(cuda_device):
         got = fe.extract(pcm, n_valid=nv).cpu().numpy()
         for i, ref in enumerate(refs):
             assert np.abs(got[i] - ref).max() <= TOL, f"iteration {it}, row {i} (len {lens[i]})"
+
+
+def test_full_size_properties_b256_128mel(cuda_device):
+    """BASELINE.json configs[2] front end at full size (256 x 30 s, 128 bins): per-row properties the domain offers —
+    every row spans exactly [max - 2, max] after the clamp + affine map, a row's features do not depend on the batch
+    around it, the bf16 time-major copy is the rounding of the fp32 features, and 8 sampled rows match the oracle."""
+    import torch
+
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(1234)
+    pcm = (0.1 * torch.randn((256, 480000), device=dev, generator=g)).clamp_(-1, 1)
+    pcm[3, 100000:] *= 1e-6                       # one row with a clamped tail
+    fe = _fe(128)
+    feats, tm = fe.extract(pcm, return_time_major=True)
+    assert feats.shape == (256, 128, 3000) and tm.shape[:2] == (256, 3000)
+    mx = feats.amax(dim=(1, 2))
+    mn = feats.amin(dim=(1, 2))
+    assert bool((mn >= mx - 2.0 - 1e-6).all())
+    assert float(mn[3]) == pytest.approx(float(mx[3]) - 2.0, abs=1e-6)
+    assert torch.equal(tm[..., :128], feats.transpose(1, 2).to(torch.bfloat16))
+    for r in (0, 3, 255):
+        assert torch.equal(fe.extract(pcm[r: r + 1].contiguous())[0], feats[r])
+    host = pcm.cpu().numpy()
+    for r in (0, 3, 37, 64, 128, 200, 254, 255):
+        assert np.abs(feats[r].cpu().numpy() - OF.log_mel(host[r], 128)).max() <= TOL, f"row {r}"
