@@ -35,6 +35,7 @@ constexpr int kSpan = kHop * (kTileFrames - 1) + kNfft;  // 5360 samples per til
 constexpr int kTStride = 500;                  // per-group stride of the transpose buffer (== 20 mod 32)
 constexpr int kTRow = 25;                      // k1 stride inside a group (== 1 mod 8, >= 20)
 constexpr int kPwPitch = 33;                   // power spectra [bin][frame], odd pitch
+static_assert(kPwPitch * 4 == kPowerPitchBytes, "mel program offsets");
 static_assert(kNfreq * kPwPitch <= kGroups * kTStride, "power spectra must fit in the transpose buffer");
 constexpr float kMelFloor = 1e-10f;
 constexpr float kLog10Floor = -10.0f;
@@ -256,17 +257,21 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         int m = s.mel_m0[wrp];
         float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
         __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
-        const float* pw = &s.tr[lane];
+        const unsigned char* pw = reinterpret_cast<const unsigned char*>(&s.tr[lane]);
         float acc_a = 0.f, acc_b = 0.f;
-        const int op_end = s.mel_op_off[wrp + 1];
-        for (int i = s.mel_op_off[wrp]; i < op_end; ++i) {
-          const int4 op = s.mel_ops[i];
-          const float p = pw[op.x * kPwPitch];
+        const int4* op_ptr = &s.mel_ops[s.mel_op_off[wrp]];
+        const int4* const op_end = &s.mel_ops[s.mel_op_off[wrp + 1]];
+        for (; op_ptr < op_end; ++op_ptr) {
+          const int4 op = *op_ptr;
+          const float p = *reinterpret_cast<const float*>(pw + op.x);
           acc_a = fmaf(__int_as_float(op.y), p, acc_a);
           acc_b = fmaf(__int_as_float(op.z), p, acc_b);
-          for (int e = 0; e < op.w; ++e) {
-            // (log10 + 4) / 4 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate); the floor is returned exactly
-            const float v = acc_a > kMelFloor ? fmaf(__log2f(acc_a), kLog2ToY, 1.0f) : kYFloor;
+          if (op.w) {  // filter complete
+            // (log10 + 4) / 4 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate; acc_a > 1e-10 is a normal
+            // number, so the flush-to-zero form needs no denormal path); the floor is returned exactly
+            float lg;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(acc_a));
+            const float v = acc_a > kMelFloor ? fmaf(lg, kLog2ToY, 1.0f) : kYFloor;
             if (live) {
               *out_ptr = v;
               tmax = fmaxf(tmax, v);
@@ -287,11 +292,12 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         const uint32_t* stw = reinterpret_cast<const uint32_t*>(&s.ti[0]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(tmajor + (static_cast<long long>(b) * n_frames + t0) * tmajor_ld);
         const int nrows = min(kTileFrames, n_frames - t0);
-        for (int idx = tid; idx < nrows * wpr; idx += kThreads) {
-          const int f = idx / wpr, wi = idx - f * wpr;
-          uint32_t v = stw[f * (wpr + 1) + wi];
-          if (2 * wi + 1 >= n_mels) v = (2 * wi < n_mels) ? (v & 0xffffu) : 0u;
-          dst[static_cast<long long>(f) * wpr + wi] = v;
+        for (int f = tid >> 5; f < nrows; f += kThreads / 32) {      // one warp per frame row, lanes along the channels
+          for (int wi = tid & 31; wi < wpr; wi += 32) {
+            uint32_t v = stw[f * (wpr + 1) + wi];
+            if (2 * wi + 1 >= n_mels) v = (2 * wi < n_mels) ? (v & 0xffffu) : 0u;
+            dst[static_cast<long long>(f) * wpr + wi] = v;
+          }
         }
         // (the next writer of ti is the next tile's pass 1, behind the block barrier of the tile-min reduction below)
       }

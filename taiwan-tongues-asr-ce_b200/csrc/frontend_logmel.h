@@ -9,12 +9,13 @@ namespace ttasr {
 constexpr int kMaxMels = 128;
 constexpr int kMelWarps = 10;    // warps of the frames kernel (320 threads); each owns a contiguous range of filters
 constexpr int kMaxMelOps = 512;  // entries of the streaming mel program (one per frequency bin walked, per warp)
+constexpr int kPowerPitchBytes = 33 * 4;  // row pitch of the [bin][frame] power-spectrum buffer the program indexes
 
 // device-resident constant tables owned by the front-end handle
 struct FrontTables {
   const float2* twiddle;  // [400]  W400^(n2*k1) = (cos, -sin)(2 pi n2 k1 / 400) at [k1*20 + n2]
   const float* window;    // [400]  periodic Hann
-  const int4* mel_ops;    // [kMaxMelOps] {bin, weight of filter m_cur, weight of filter m_cur + 1, filters completed}
+  const int4* mel_ops;    // [kMaxMelOps] {bin * kPowerPitchBytes, weight of filter m_cur, of m_cur + 1, 1 = emit a filter}
   const int* mel_op_off;  // [kMelWarps + 1] warp w runs ops [mel_op_off[w], mel_op_off[w + 1])
   const int* mel_m0;      // [kMelWarps + 1] warp w owns filters [mel_m0[w], mel_m0[w + 1])
 };

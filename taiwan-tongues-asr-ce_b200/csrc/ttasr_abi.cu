@@ -170,11 +170,13 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
         k_end = std::max(k_end, last[m]);
       }
     int m_cur = m0;
-    auto emit_into_last = [&](int n) {  // n more filters are complete
-      if (n <= 0) return;
-      if (static_cast<int>(ops.size()) == op_off[w]) ops.push_back(make_int4(0, 0, 0, 0));  // nothing walked yet
-      ops.back().w += n;
-      m_cur += n;
+    // n more filters are complete: the flag goes on the last op; further completions (empty filters, narrow
+    // triangles) get weightless ops of their own, so the kernel only ever tests "emit one filter after this op"
+    auto emit_into_last = [&](int n) {
+      for (; n > 0; --n, ++m_cur) {
+        if (static_cast<int>(ops.size()) == op_off[w] || ops.back().w != 0) ops.push_back(make_int4(0, 0, 0, 0));
+        ops.back().w = 1;
+      }
     };
     for (int k = k_begin; k <= k_end && m_cur < m1; ++k) {
       int done = 0;  // filters (from m_cur on) whose last non-zero bin lies before k
@@ -189,7 +191,7 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
       const float wa = weight(k, m_cur);
       const float wb = (m_cur + 1 < m1) ? weight(k, m_cur + 1) : 0.f;
       int4 op;
-      op.x = k;
+      op.x = k * kPowerPitchBytes;  // byte offset of the bin's row in the power-spectrum buffer
       memcpy(&op.y, &wa, 4);
       memcpy(&op.z, &wb, 4);
       op.w = 0;
