@@ -44,13 +44,16 @@ class FileFeatureExtractor:
         F = self.nb_max_frames - 3
         n_chunks = max(1, -(-n_frames // F))
         rows = np.zeros((n_chunks, N), np.float32)
+        lens = np.zeros(n_chunks, np.int32)
         leads = [0] + [2] * (n_chunks - 1)
         for c in range(n_chunks):
             start = (c * F - leads[c]) * hop
             seg = x[start: start + N]
             rows[c, : seg.shape[0]] = seg
+            lens[c] = seg.shape[0]
         dev = self.fe._torch_device()
-        feats = self.fe.extract(torch.from_numpy(rows).to(dev))  # per-chunk clamp, (x + 4) / 4
+        # per-chunk clamp, (x + 4) / 4; the zero tail of the last row is declared as padding so its tiles skip the FFT
+        feats = self.fe.extract(torch.from_numpy(rows).to(dev), n_valid=torch.from_numpy(lens).to(dev))
         raw = torch.as_tensor(feats) * 4.0 - 4.0                  # back to (chunk-clamped) log10
         # the per-chunk clamp only raises values to (chunk max - 8) <= (file max - 8), so clamping again with the
         # file maximum gives exactly the whole-file result
