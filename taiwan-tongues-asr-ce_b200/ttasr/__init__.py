@@ -8,9 +8,9 @@ from . import decode_handoff  # noqa: F401
 from .encoder import B200WhisperEncoder, EncoderConfig  # noqa: F401
 from .feature_extractor import B200WhisperFeatureExtractor  # noqa: F401
 from .ingest import B200AudioIngest, resample_poly_filter  # noqa: F401
-from .pipeline import B200LogMelEncoder  # noqa: F401
+from .pipeline import B200LogMelEncoder, GraphedLogMelEncoder  # noqa: F401
 
 __all__ = [
-    "B200WhisperFeatureExtractor", "B200WhisperEncoder", "EncoderConfig", "B200LogMelEncoder", "B200AudioIngest", "resample_poly_filter",
+    "B200WhisperFeatureExtractor", "B200WhisperEncoder", "EncoderConfig", "B200LogMelEncoder", "GraphedLogMelEncoder", "B200AudioIngest", "resample_poly_filter",
     "TtasrError", "abi_version", "library_path",
 ]

@@ -45,10 +45,22 @@ def pcm_bytes_to_tensor(buf, samples_width: int = 2):
 class MicroBatcher:
     """Collects utterances for at most `window_s` (or until `max_batch`) and encodes them in one launch."""
 
-    def __init__(self, pipeline: B200LogMelEncoder, window_s: float = 0.005, max_batch: int = 64):
+    def __init__(self, pipeline: B200LogMelEncoder, window_s: float = 0.005, max_batch: int = 64,
+                 use_graphs: bool = False):
+        """use_graphs: replay one CUDA graph per batch-size bucket (pipeline.GraphedLogMelEncoder) instead of issuing
+        the ~230 launches of a forward from the event loop."""
         self.pipeline = pipeline
         self.window_s = window_s
         self.max_batch = max_batch
+        self.graphed = None
+        if use_graphs:
+            from .pipeline import GraphedLogMelEncoder
+
+            # dense at the small end, where a padded row costs a visible share of the launch
+            ladder = list(range(1, 9)) + list(range(10, 17, 2)) + list(range(20, 33, 4)) + list(range(40, 65, 8)) + \
+                list(range(80, 257, 16))
+            buckets = [b for b in ladder if b < max_batch] + [max_batch]
+            self.graphed = GraphedLogMelEncoder(pipeline, buckets)
         self.n_samples = pipeline.feature_extractor.n_samples
         self._pending: list[Utterance] = []
         self._flusher = None
@@ -61,6 +73,11 @@ class MicroBatcher:
 
         B = len(utterances)
         lens = [min(int(u.pcm_i16.numel()), self.n_samples) for u in utterances]
+        if self.graphed is not None:
+            hidden = self.graphed.encode([u.pcm_i16 for u in utterances], lens)
+            self.launches += 1
+            self.encoded += B
+            return hidden, lens
         width = max(max(lens), 1)
         width = (width + 7) // 8 * 8  # 16-byte rows keep the bulk-copy path
         host = torch.zeros((B, width), dtype=torch.int16).pin_memory()
@@ -108,13 +125,14 @@ class B200ASR:
     """ASRInterface implementation (duck-typed: `async transcribe(client)`, `warm_up()`)."""
 
     def __init__(self, pipeline: B200LogMelEncoder, decode_fn: Callable[[Any, dict], dict],
-                 batch_window_s: float = 0.005, max_batch: int = 64, language: str = "zh", **kwargs):
+                 batch_window_s: float = 0.005, max_batch: int = 64, language: str = "zh",
+                 use_graphs: bool = False, **kwargs):
         """decode_fn(hidden [1, 1500, d] CUDA bf16, info dict) -> {"text": str, "words": [...], "language": ...,
         "language_probability": ...}; it owns beam search and text post-processing exactly as the reference's
         decoder does today."""
         self.pipeline = pipeline
         self.decode_fn = decode_fn
-        self.batcher = MicroBatcher(pipeline, batch_window_s, max_batch)
+        self.batcher = MicroBatcher(pipeline, batch_window_s, max_batch, use_graphs=use_graphs)
         self.language = language
         self.device = "cuda"
         self.compute_type = "bfloat16"
@@ -156,5 +174,6 @@ class B200ASR:
         t0 = time.time()
         utt = Utterance(torch.zeros(16000, dtype=torch.int16), None)
         hidden, _ = self.batcher.encode_batch([utt])
+        graphs = self.batcher.graphed.build_all() if self.batcher.graphed is not None else 0
         torch.cuda.synchronize(self.pipeline.device)
-        return {"warm_up_seconds": time.time() - t0, "hidden_shape": tuple(hidden.shape)}
+        return {"warm_up_seconds": time.time() - t0, "hidden_shape": tuple(hidden.shape), "cuda_graphs": graphs}

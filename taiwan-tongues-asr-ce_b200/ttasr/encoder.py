@@ -171,10 +171,19 @@ class B200WhisperEncoder:
 
         need = self.workspace_bytes(batch)
         if self._ws is None or self._ws.numel() < need + 1024:
+            # growing replaces the buffer: anything that baked the old address in (a captured CUDA graph) is stale
+            # from here on — `workspace_generation` lets such holders notice; reserve_workspace() avoids it up front
             self._ws = None
             self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            self.workspace_generation = getattr(self, "workspace_generation", 0) + 1
         off = (-self._ws.data_ptr()) % 1024
         return self._ws.data_ptr() + off, need
+
+    def reserve_workspace(self, max_batch: int) -> int:
+        """Size the cached workspace for `max_batch` chunks now, so that later calls up to that batch never reallocate
+        it (required before capturing CUDA graphs of encode()).  Returns the generation counter of the buffer."""
+        self._workspace(max_batch)
+        return getattr(self, "workspace_generation", 0)
 
     def encode(self, input_features, out_dtype=None, time_major_ld: int | None = None):
         """[B, n_mels, 3000] float32 (numpy / torch, host or device) -> [B, 1500, d] (bf16 by default) on the GPU.

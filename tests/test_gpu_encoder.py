@@ -119,7 +119,8 @@ def test_pipelined_host_stream_matches_single_calls(cuda_device):
         assert torch.equal(o, ref)
 
 
-def test_streaming_plugin_end_to_end(cuda_device):
+@pytest.mark.parametrize("use_graphs", [False, True])
+def test_streaming_plugin_end_to_end(cuda_device, use_graphs):
     """B200ASR (the reference's ASRInterface): int16 scratch buffers of several clients -> one batched launch ->
     hidden states identical to encoding each utterance alone; decode stays with the host callback."""
     import asyncio
@@ -136,7 +137,7 @@ def test_streaming_plugin_end_to_end(cuda_device):
         seen[info["n_samples"]] = hidden.float().cpu()
         return {"text": "測試", "words": []}
 
-    asr = B200ASR(pipe, decode, batch_window_s=0.02)
+    asr = B200ASR(pipe, decode, batch_window_s=0.02, max_batch=8, use_graphs=use_graphs)
     assert asr.warm_up()["hidden_shape"] == (1, 1500, arch.d_model)
     rng = np.random.default_rng(8)
     pcm = [(rng.standard_normal(n) * 2000).astype("<i2") for n in (16000, 52345, 80000)]
@@ -257,3 +258,48 @@ def test_full_size_properties_large_v3_b256(cuda_device):
     perm = torch.randperm(B, device=dev, generator=g)
     hp = pipe.encode_device(pcm[perm].contiguous(), n_valid=nv[perm].contiguous())
     assert torch.equal(hp, h1[perm])
+
+
+def test_graph_buckets_match_eager_for_ragged_micro_batches(cuda_device):
+    """Serving path: replaying one CUDA graph per batch-size bucket gives exactly the eager result for ragged int16
+    utterances, across buckets, repeated replays and padded (empty) rows."""
+    import torch
+    from ttasr import B200LogMelEncoder, B200WhisperFeatureExtractor, GraphedLogMelEncoder
+
+    arch, w, enc = _build("micro")
+    pipe = B200LogMelEncoder(B200WhisperFeatureExtractor(feature_size=arch.n_mels), enc)
+    graphed = GraphedLogMelEncoder(pipe, buckets=(1, 2, 4))
+    rng = np.random.default_rng(3)
+    for lens in ([16000], [80000, 24000, 50001], [48000, 16000], [1], [33333, 480000, 7, 160]):
+        rows = [torch.from_numpy((rng.standard_normal(n) * 3000).astype(np.int16)) for n in lens]
+        got = graphed.encode(rows)
+        width = (max(lens) + 7) // 8 * 8
+        host = torch.zeros((len(lens), width), dtype=torch.int16)
+        for i, r in enumerate(rows):
+            host[i, : lens[i]] = r
+        ref = pipe.encode_device(host.to(cuda_device), n_valid=torch.tensor(lens, dtype=torch.int32, device=cuda_device))
+        assert got.shape == ref.shape and torch.equal(got, ref), lens
+    assert graphed.replays == 5 and sorted(graphed._graphs) == [1, 2, 4]
+    with pytest.raises(Exception):
+        graphed.encode([torch.zeros(10, dtype=torch.int16)] * 5)
+
+
+def test_graph_buckets_survive_workspace_growth(cuda_device):
+    """A larger eager batch after capture replaces the encoder's cached workspace; the graph holder must notice and
+    re-capture instead of replaying graphs that point at the freed buffer."""
+    import torch
+    from ttasr import B200LogMelEncoder, B200WhisperFeatureExtractor, GraphedLogMelEncoder
+
+    arch, w, enc = _build("micro")
+    pipe = B200LogMelEncoder(B200WhisperFeatureExtractor(feature_size=arch.n_mels), enc)
+    graphed = GraphedLogMelEncoder(pipe, buckets=(1, 2))
+    rng = np.random.default_rng(4)
+    row = torch.from_numpy((rng.standard_normal(40000) * 3000).astype(np.int16))
+    first = graphed.encode([row])
+    gen = enc.workspace_generation
+    big = torch.from_numpy((rng.standard_normal((6, 480000)) * 3000).astype(np.int16)).to(cuda_device)
+    pipe.encode_device(big)                                  # grows the workspace past the reservation
+    assert enc.workspace_generation > gen
+    torch.empty(64 << 20, dtype=torch.uint8, device=cuda_device).fill_(0xAB)   # scribble over whatever was freed
+    again = graphed.encode([row])
+    assert torch.equal(first, again)
