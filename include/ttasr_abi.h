@@ -19,6 +19,10 @@
  *     thread-local message for the last failing call on this thread.
  *   - all device work is ordered on the `stream` argument (a cudaStream_t passed as void*); calls are asynchronous.
  *   - handles are immutable after create, usable from any thread, one per device (the device current at create).
+ *     Exception: a front-end handle owns the per-call scratch of its kernels (per-chunk maxima, per-tile minima), so
+ *     calls of ttasr_frontend_run on ONE handle must be ordered (same stream, or serialised by the caller); use one
+ *     handle per concurrent stream.  Encoder calls take their workspace from the caller and may run concurrently
+ *     with distinct workspaces.  ttasr_ingest_* keeps no per-call state.
  *   - create fails with TTASR_E_ARCH on anything but compute capability 10.x: there is no fallback path.
  */
 #ifndef TTASR_ABI_H_
@@ -77,7 +81,7 @@ TTASR_API int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_sample
 TTASR_API int ttasr_frontend_run(const ttasr_frontend_t* h, const void* pcm_dev, int pcm_dtype, int64_t batch,
                        int64_t row_stride, const int32_t* n_valid_dev, float* feats_dev, void* tmajor_dev,
                        int tmajor_ld, void* stream);
-/* bytes of scratch (per-chunk maxima) the handle keeps per batch element; informational */
+/* largest batch one ttasr_frontend_run call accepts (sizes the handle's scratch: per-chunk maxima, per-tile minima) */
 TTASR_API int ttasr_frontend_max_batch(const ttasr_frontend_t* h, int64_t* out);
 TTASR_API void ttasr_frontend_destroy(ttasr_frontend_t* h);
 
