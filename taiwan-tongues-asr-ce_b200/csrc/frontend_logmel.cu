@@ -19,7 +19,8 @@
 // transformed, so every PCM byte is read from HBM once (+4.5 % halo, L2 hits).  Twenty threads own one pair of
 // frames: 400 = 20 x 20, each thread a register-resident twiddle-free 20-point PFA DFT (fft400.cuh), one
 // shared-memory transpose between the passes (strides chosen bank-conflict-free), then Hermitian split, power,
-// a gather over the <= 2-nonzero-per-bin mel filters, log10, and 128-byte coalesced stores along time.
+// the mel projection as a host-built streaming program (a bin feeds <= 2 adjacent triangles: each warp walks the bins
+// of its filter range once with two accumulators), lg2, and 128-byte coalesced stores along time.
 #include "fft400.cuh"
 #include "frontend_logmel.h"
 #include "ptx_sm100.cuh"
