@@ -60,6 +60,16 @@ struct GemmParams {
   int tiles_n;
   int num_tiles;
   int add_bcast;
+  // ---- optional LayerNorm fusion (see GemmCall)
+  __nv_bfloat16* ln_xb;        // producer side: bf16 copy of the fp32 output rows
+  float2* ln_stats_out;        // producer side: per-row partial (sum, sum of squares): [row][2 * tiles_n]
+  const float2* ln_stats_in;   // consumer side: partials of the A operand's rows: [row][ln_parts_in]
+  const float* ln_c1;          // consumer side: [n] column sums of the gamma-folded weights
+  int ln_parts_in;
+  float ln_inv_k;              // 1 / (normalised width)
+  float ln_eps;
+  int rows;                    // output rows per batch item
+  int n;                       // output columns
 };
 
 __device__ __forceinline__ void lds128(uint32_t addr, float4& v) {
@@ -269,6 +279,29 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
       mbar_wait(tfull_bar(as), aphase);
       tc_fence_after();
       const uint32_t acc_addr = tmem_base + lane_base + as * BN;
+      // ---- LayerNorm fusion, per tile: this thread owns output row (b, t0 + row)
+      const bool row_ok = (t0 + row) < p.rows;
+      const long long grow = static_cast<long long>(b) * p.rows + t0 + row;
+      const bool ln_emit = OUT_F32 && (p.ln_stats_out != nullptr);
+      float ln_s1 = 0.f, ln_s2 = 0.f;
+      __nv_bfloat16* ln_xb_row = ln_emit ? p.ln_xb + grow * p.n : nullptr;
+      float ln_a = 1.f, ln_b = 0.f;      // consumer side: out = ln_a * acc + ln_b * c1[n] + c2[n]
+      const bool ln_in = !OUT_F32 && (p.ln_stats_in != nullptr);
+      if (ln_in) {
+        float s1 = 0.f, s2 = 0.f;
+        if (row_ok) {
+          const float2* st = p.ln_stats_in + grow * p.ln_parts_in;
+          for (int i = 0; i < p.ln_parts_in; ++i) {  // fixed order: bit-reproducible statistics
+            const float2 t = __ldg(st + i);
+            s1 += t.x;
+            s2 += t.y;
+          }
+        }
+        const float mean = s1 * p.ln_inv_k;
+        const float var = fmaxf(fmaf(s2, p.ln_inv_k, -mean * mean), 0.f);
+        ln_a = rsqrtf(var + p.ln_eps);
+        ln_b = -ln_a * mean;
+      }
 #pragma unroll 1
       for (int s = wg; s < kNSlab; s += 2) {
         const uint32_t q = q0 + s;
@@ -289,6 +322,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
           if (HAS_ADD) mbar_wait(add_full(buf), use);         // addend slab landed (prefetched by warp 3)
           else mbar_wait(buf_free(buf), use ^ 1);             // slab recycled by the store thread
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 32);
+          uint32_t xbw[16];  // bf16 copy of this row's 32 columns (LayerNorm fusion only)
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 bv = __ldg(bias4 + c);
@@ -317,6 +351,17 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
               }
             }
             sts128(addr, v);
+            if (ln_emit) {
+              ln_s1 += (v.x + v.y) + (v.z + v.w);
+              ln_s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ln_s2))));
+              xbw[2 * c] = pack_bf16x2(v.x, v.y);
+              xbw[2 * c + 1] = pack_bf16x2(v.z, v.w);
+            }
+          }
+          if (ln_emit && row_ok) {
+            uint4* dst = reinterpret_cast<uint4*>(ln_xb_row + n0 + s * 32);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(xbw[4 * c], xbw[4 * c + 1], xbw[4 * c + 2], xbw[4 * c + 3]);
           }
         } else {
           uint32_t acc0[32], acc1[32];
@@ -333,33 +378,50 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 16-byte chunk = 8 bf16 columns
             const uint32_t* a = (c < 4) ? &acc0[8 * c] : &acc1[8 * (c - 4)];
-            const float4 b0 = __ldg(bias4 + 2 * c), b1 = __ldg(bias4 + 2 * c + 1);
+            float4 b0 = __ldg(bias4 + 2 * c), b1 = __ldg(bias4 + 2 * c + 1);
+            uint32_t aa[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) aa[i] = a[i];
+            if (ln_in) {  // LayerNorm folded in: x = ln_a * acc + (ln_b * c1 + c2); the code below then adds "bias" 0
+              const float4* c14 = reinterpret_cast<const float4*>(p.ln_c1 + n0 + s * 64);
+              const float4 k0 = __ldg(c14 + 2 * c), k1 = __ldg(c14 + 2 * c + 1);
+              const f32x2_t pa = pack2(ln_a, ln_a), pb = pack2(ln_b, ln_b);
+              float r[8];
+              unpack2(fma2(pa, pack2(__uint_as_float(a[0]), __uint_as_float(a[1])), fma2(pb, pack2(k0.x, k0.y), pack2(b0.x, b0.y))), r[0], r[1]);
+              unpack2(fma2(pa, pack2(__uint_as_float(a[2]), __uint_as_float(a[3])), fma2(pb, pack2(k0.z, k0.w), pack2(b0.z, b0.w))), r[2], r[3]);
+              unpack2(fma2(pa, pack2(__uint_as_float(a[4]), __uint_as_float(a[5])), fma2(pb, pack2(k1.x, k1.y), pack2(b1.x, b1.y))), r[4], r[5]);
+              unpack2(fma2(pa, pack2(__uint_as_float(a[6]), __uint_as_float(a[7])), fma2(pb, pack2(k1.z, k1.w), pack2(b1.z, b1.w))), r[6], r[7]);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) aa[i] = __float_as_uint(r[i]);
+              b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+              b1 = b0;
+            }
             if constexpr (ACT == 1 && TTASR_GELU_F32X2) {
-              const uint32_t o0 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack2(b0.x, b0.y)));
-              const uint32_t o1 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(a[2]), __uint_as_float(a[3])), pack2(b0.z, b0.w)));
-              const uint32_t o2 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack2(b1.x, b1.y)));
-              const uint32_t o3 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(a[6]), __uint_as_float(a[7])), pack2(b1.z, b1.w)));
+              const uint32_t o0 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(aa[0]), __uint_as_float(aa[1])), pack2(b0.x, b0.y)));
+              const uint32_t o1 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(aa[2]), __uint_as_float(aa[3])), pack2(b0.z, b0.w)));
+              const uint32_t o2 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(aa[4]), __uint_as_float(aa[5])), pack2(b1.x, b1.y)));
+              const uint32_t o3 = gelu_erf_bf16x2(add2(pack2(__uint_as_float(aa[6]), __uint_as_float(aa[7])), pack2(b1.z, b1.w)));
               sts128u(slab + row_off + ((c ^ swz) << 4), o0, o1, o2, o3);
               continue;
             }
             if constexpr (ACT == 0 && TTASR_GELU_F32X2) {
               float r[8];
-              unpack2(add2(pack2(__uint_as_float(a[0]), __uint_as_float(a[1])), pack2(b0.x, b0.y)), r[0], r[1]);
-              unpack2(add2(pack2(__uint_as_float(a[2]), __uint_as_float(a[3])), pack2(b0.z, b0.w)), r[2], r[3]);
-              unpack2(add2(pack2(__uint_as_float(a[4]), __uint_as_float(a[5])), pack2(b1.x, b1.y)), r[4], r[5]);
-              unpack2(add2(pack2(__uint_as_float(a[6]), __uint_as_float(a[7])), pack2(b1.z, b1.w)), r[6], r[7]);
+              unpack2(add2(pack2(__uint_as_float(aa[0]), __uint_as_float(aa[1])), pack2(b0.x, b0.y)), r[0], r[1]);
+              unpack2(add2(pack2(__uint_as_float(aa[2]), __uint_as_float(aa[3])), pack2(b0.z, b0.w)), r[2], r[3]);
+              unpack2(add2(pack2(__uint_as_float(aa[4]), __uint_as_float(aa[5])), pack2(b1.x, b1.y)), r[4], r[5]);
+              unpack2(add2(pack2(__uint_as_float(aa[6]), __uint_as_float(aa[7])), pack2(b1.z, b1.w)), r[6], r[7]);
               sts128u(slab + row_off + ((c ^ swz) << 4), pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]),
                       pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
               continue;
             }
-            const float v0 = apply_act<ACT>(__uint_as_float(a[0]) + b0.x);
-            const float v1 = apply_act<ACT>(__uint_as_float(a[1]) + b0.y);
-            const float v2 = apply_act<ACT>(__uint_as_float(a[2]) + b0.z);
-            const float v3 = apply_act<ACT>(__uint_as_float(a[3]) + b0.w);
-            const float v4 = apply_act<ACT>(__uint_as_float(a[4]) + b1.x);
-            const float v5 = apply_act<ACT>(__uint_as_float(a[5]) + b1.y);
-            const float v6 = apply_act<ACT>(__uint_as_float(a[6]) + b1.z);
-            const float v7 = apply_act<ACT>(__uint_as_float(a[7]) + b1.w);
+            const float v0 = apply_act<ACT>(__uint_as_float(aa[0]) + b0.x);
+            const float v1 = apply_act<ACT>(__uint_as_float(aa[1]) + b0.y);
+            const float v2 = apply_act<ACT>(__uint_as_float(aa[2]) + b0.z);
+            const float v3 = apply_act<ACT>(__uint_as_float(aa[3]) + b0.w);
+            const float v4 = apply_act<ACT>(__uint_as_float(aa[4]) + b1.x);
+            const float v5 = apply_act<ACT>(__uint_as_float(aa[5]) + b1.y);
+            const float v6 = apply_act<ACT>(__uint_as_float(aa[6]) + b1.z);
+            const float v7 = apply_act<ACT>(__uint_as_float(aa[7]) + b1.w);
             sts128u(slab + row_off + ((c ^ swz) << 4), pack_bf16x2(v0, v1), pack_bf16x2(v2, v3), pack_bf16x2(v4, v5),
                     pack_bf16x2(v6, v7));
           }
@@ -368,6 +430,8 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
         __syncwarp();
         if (lane == 0) mbar_arrive(out_ready(buf));
       }
+      if (ln_emit && row_ok)
+        p.ln_stats_out[grow * (2 * p.tiles_n) + (n0 / BN) * 2 + wg] = make_float2(ln_s1, ln_s2);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -492,6 +556,28 @@ cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, con
   p.tiles_n = c.n / bn;
   p.num_tiles = p.tiles_m_per_batch * c.nbatch * p.tiles_n;
   p.add_bcast = c.addend_bcast;
+  p.rows = c.rows;
+  p.n = c.n;
+  if (c.ln_stats_out) {
+    if (!c.out_f32 || !c.ln_xb || (reinterpret_cast<uintptr_t>(c.ln_xb) & 15) || (reinterpret_cast<uintptr_t>(c.ln_stats_out) & 7)) {
+      *why = "gemm: LayerNorm emit needs fp32 output and 16-byte aligned ln_xb";
+      return cudaErrorInvalidValue;
+    }
+    p.ln_xb = static_cast<__nv_bfloat16*>(c.ln_xb);
+    p.ln_stats_out = static_cast<float2*>(c.ln_stats_out);
+    if (c.ln_parts_out) *c.ln_parts_out = 2 * p.tiles_n;
+  }
+  if (c.ln_stats_in) {
+    if (c.out_f32 || !c.ln_c1 || c.ln_parts_in <= 0 || c.mode != kGemmPlain) {
+      *why = "gemm: LayerNorm-folded input needs bf16 output, ln_c1 and ln_parts_in";
+      return cudaErrorInvalidValue;
+    }
+    p.ln_stats_in = static_cast<const float2*>(c.ln_stats_in);
+    p.ln_c1 = c.ln_c1;
+    p.ln_parts_in = c.ln_parts_in;
+    p.ln_inv_k = 1.0f / static_cast<float>(c.a_inner);
+    p.ln_eps = c.ln_eps;
+  }
 
   CUresult r;
   {  // A: (channel, parity, row, batch)

@@ -33,6 +33,19 @@ struct GemmCall {
   void* out = nullptr;              // [nbatch*rows, n]
   int out_f32 = 0;
   int cta_group = 0;                // 0 = default, 1, 2
+  // ---- optional LayerNorm fusion.  A residual GEMM (fp32 out) can EMIT what the LayerNorm of its output needs: a
+  // bf16 copy of the rows (ln_xb, [nbatch*rows, n]) and, per row, 2 * (n / tile width) partial (sum, sum of squares)
+  // pairs (ln_stats_out; *ln_parts_out receives the count).  The GEMM that consumes LN(x) W^T then runs on the bf16
+  // copy with gamma folded into W and applies  out = rstd * (acc - mean * c1[n]) + bias[n]  in its epilogue (bf16 out),
+  // c1[n] = sum_k W'[n][k], bias[n] = b[n] + sum_k beta[k] W[n][k]; mean / rstd come from the partials (ln_stats_in,
+  // ln_parts_in per row, summed in a fixed order).
+  void* ln_xb = nullptr;
+  void* ln_stats_out = nullptr;
+  int* ln_parts_out = nullptr;
+  const void* ln_stats_in = nullptr;
+  int ln_parts_in = 0;
+  const float* ln_c1 = nullptr;
+  float ln_eps = 1e-5f;
 };
 
 // TMA descriptor helper (driver entry point resolved at run time; libcuda is not linked)

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,6 +57,32 @@ __global__ void scale_copy_bf16_kernel(__nv_bfloat16* dst, const __nv_bfloat16* 
 __global__ void scale_copy_f32_kernel(float* dst, const float* src, long long n, float scale) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src ? src[i] * scale : 0.f;
+}
+// LayerNorm folded into the consuming projection:  LN(x) W^T + b = rstd * (x W'^T - mean * c1) + c2  with
+// W'[n][k] = bf16(scale * W[n][k] * gamma[k]),  c1[n] = sum_k W'[n][k] (of the ROUNDED weights, as the MMA sees them),
+// c2[n] = scale * b[n] + sum_k beta[k] * scale * W[n][k].  One warp per output row n.
+__global__ void fold_ln_kernel(__nv_bfloat16* dst, const __nv_bfloat16* src, int n_rows, int k, float scale,
+                               const float* gamma, const float* beta, const float* bias, float* c1, float* c2) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= n_rows) return;
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = lane; j < k; j += 32) {
+    const float w = __bfloat162float(src[static_cast<size_t>(n) * k + j]) * scale;
+    const __nv_bfloat16 wf = __float2bfloat16(w * gamma[j]);
+    dst[static_cast<size_t>(n) * k + j] = wf;
+    s1 += __bfloat162float(wf);
+    s2 = fmaf(beta[j], w, s2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  if (lane == 0) {
+    c1[n] = s1;
+    c2[n] = s2 + (bias ? bias[n] * scale : 0.f);
+  }
 }
 // conv weight [n_out, c_in, 3] -> tap-major [n_out, 3 * c_pad] (zero padded channels)
 __global__ void pack_conv_kernel(__nv_bfloat16* dst, const __nv_bfloat16* src, int n_out, int c_in, int c_pad) {
@@ -356,7 +383,14 @@ void ttasr_ingest_destroy(ttasr_ingest_t* h) {
 struct LayerDev {
   const float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *b1, *b2;
   const __nv_bfloat16 *wqkv, *wo, *w1, *w2;
+  // LayerNorm-fused mode: wqkv / w1 hold the gamma-folded weights, bqkv / b1 the folded biases (c2), and
+  const float *c1_qkv = nullptr, *c1_fc1 = nullptr;   // column sums of the folded weights
 };
+
+#ifndef TTASR_FUSE_LN_DEFAULT
+#define TTASR_FUSE_LN_DEFAULT 0
+#endif
+constexpr bool kFuseLnDefault = TTASR_FUSE_LN_DEFAULT != 0;
 
 enum ProfileKind { kProfPrep = 0, kProfConv1, kProfConv2, kProfLayerNorm, kProfQkv, kProfAttention, kProfOutProj,
                    kProfFc1, kProfFc2, kProfKinds };
@@ -384,6 +418,7 @@ struct ttasr_encoder {
   int device = 0, num_sms = 0;
   ttasr_encoder_cfg cfg{};
   int c1_pad = 128;        // conv1 input channels padded per tap
+  bool fuse_ln = false;    // per-layer LayerNorms folded into the QKV / fc1 GEMMs (TTASR_FUSE_LN, see encoder_create)
   void* arena = nullptr;   // all packed weights
   const __nv_bfloat16 *conv1_w = nullptr, *conv2_w = nullptr;
   const float *conv1_b = nullptr, *conv2_b = nullptr, *pos = nullptr, *lnp_g = nullptr, *lnp_b = nullptr;
@@ -393,9 +428,9 @@ struct ttasr_encoder {
 namespace {
 
 struct WsLayout {
-  size_t x, h, qkv, ffn, total;
+  size_t x, h, qkv, ffn, xb, st0, st1, total;
 };
-WsLayout ws_layout(const ttasr_encoder_cfg& c, int64_t B) {
+WsLayout ws_layout(const ttasr_encoder_cfg& c, int64_t B, bool fuse_ln) {
   auto up = [](size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); };
   const size_t rows = static_cast<size_t>(B) * c.n_ctx;
   WsLayout w;
@@ -406,6 +441,13 @@ WsLayout ws_layout(const ttasr_encoder_cfg& c, int64_t B) {
   w.qkv = o; o += up(std::max(rows * 3 * c.d_model * 2, rows * 2 * 128 * 2));
   // ffn region also hosts conv1's output [B, 2*n_ctx, d] (ffn >= 2d always holds for Whisper; guarded in create)
   w.ffn = o; o += up(std::max(rows * c.ffn_dim * 2, rows * 2 * c.d_model * 2));
+  w.xb = w.st0 = w.st1 = o;
+  if (fuse_ln) {  // bf16 copy of the residual stream + two sets of per-row LayerNorm partials (<= 2 * d/128 per row)
+    const size_t parts = 2 * static_cast<size_t>(c.d_model / 128);
+    w.xb = o;  o += up(rows * c.d_model * 2);
+    w.st0 = o; o += up(rows * parts * 8);
+    w.st1 = o; o += up(rows * parts * 8);
+  }
   w.total = o;
   return w;
 }
@@ -440,13 +482,17 @@ int ttasr_encoder_create(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, t
   h->device = device;
   h->num_sms = sms;
   h->cfg = *cfg;
+  {
+    const char* env = getenv("TTASR_FUSE_LN");
+    h->fuse_ln = env ? (atoi(env) != 0) : kFuseLnDefault;
+  }
   const size_t dd = static_cast<size_t>(d) * d;
   size_t bytes = 0;
   auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
   const size_t conv1_bytes = up(static_cast<size_t>(d) * 3 * h->c1_pad * 2), conv2_bytes = up(3 * dd * 2);
   bytes += conv1_bytes + conv2_bytes + 2 * up(d * 4) + up(static_cast<size_t>(cfg->n_ctx) * d * 4) + 2 * up(d * 4);
   const size_t per_layer = up(3 * dd * 2) + up(dd * 2) + 2 * up(static_cast<size_t>(d) * f * 2) + 4 * up(d * 4) +
-                           up(3 * d * 4) + up(d * 4) + up(f * 4) + up(d * 4);
+                           up(3 * d * 4) + up(d * 4) + up(f * 4) + up(d * 4) + up(3 * d * 4) + up(f * 4);
   bytes += per_layer * L;
   cudaError_t e = cudaMalloc(&h->arena, bytes);
   if (e != cudaSuccess) { delete h; return fail(TTASR_E_NOMEM, "encoder_create: cudaMalloc(%zu) for packed weights: %s", bytes, cudaGetErrorString(e)); }
@@ -501,6 +547,22 @@ int ttasr_encoder_create(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, t
     o.b1 = copy_f32(l.b1, f, 1.f);
     o.w2 = copy_bf16(l.w2, static_cast<size_t>(d) * f, 1.f);
     o.b2 = copy_f32(l.b2, d, 1.f);
+    if (h->fuse_ln) {
+      // fold LN1 into the fused QKV projection and LN2 into fc1, in place of the plain copies made above
+      float* c1q = reinterpret_cast<float*>(take(3 * d * 4));
+      float* c1f = reinterpret_cast<float*>(take(f * 4));
+      auto fold = [&](__nv_bfloat16* dst, const void* src, int n_rows, float scale, const float* g, const float* bta,
+                      const float* bias, float* c1, float* c2) {
+        fold_ln_kernel<<<blocks_for(static_cast<long long>(n_rows) * 32, 256), 256>>>(
+            dst, static_cast<const __nv_bfloat16*>(src), n_rows, d, scale, g, bta, bias, c1, c2);
+      };
+      fold(wqkv, l.wq, d, qscale, l.ln1_g, l.ln1_b, l.bq, c1q, bqkv);
+      fold(wqkv + dd, l.wk, d, 1.f, l.ln1_g, l.ln1_b, nullptr, c1q + d, bqkv + d);
+      fold(wqkv + 2 * dd, l.wv, d, 1.f, l.ln1_g, l.ln1_b, l.bv, c1q + 2 * d, bqkv + 2 * d);
+      fold(const_cast<__nv_bfloat16*>(o.w1), l.w1, f, 1.f, l.ln2_g, l.ln2_b, l.b1, c1f, const_cast<float*>(o.b1));
+      o.c1_qkv = c1q;
+      o.c1_fc1 = c1f;
+    }
   }
   e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -520,13 +582,13 @@ int ttasr_encoder_create(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, t
 int ttasr_encoder_workspace_bytes(const ttasr_encoder_t* h, int64_t batch, size_t* out) {
   if (!h || !out) return fail(TTASR_E_ARG, "encoder_workspace_bytes: null argument");
   if (batch < 0) return fail(TTASR_E_SHAPE, "encoder_workspace_bytes: negative batch");
-  *out = ws_layout(h->cfg, batch).total;
+  *out = ws_layout(h->cfg, batch, h->fuse_ln).total;
   return TTASR_OK;
 }
 
 int ttasr_encoder_launch_count(const ttasr_encoder_t* h, int64_t* out) {
   if (!h || !out) return fail(TTASR_E_ARG, "encoder_launch_count: null argument");
-  *out = 1 + 2 + 7LL * h->cfg.n_layers + 1;
+  *out = 1 + 2 + (h->fuse_ln ? 5LL : 7LL) * h->cfg.n_layers + 1;
   return TTASR_OK;
 }
 
@@ -539,7 +601,7 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
   if (out_dtype != TTASR_OUT_BF16 && out_dtype != TTASR_OUT_F32) return fail(TTASR_E_ARG, "encoder_forward: bad out_dtype %d", out_dtype);
   const ttasr_encoder_cfg& c = h->cfg;
   if (batch * c.n_ctx * 2 > 0x7fffffffLL) return fail(TTASR_E_SHAPE, "encoder_forward: batch %lld too large for one call", (long long)batch);
-  const WsLayout ws = ws_layout(c, batch);
+  const WsLayout ws = ws_layout(c, batch, h->fuse_ln);
   if (workspace_bytes < ws.total) return fail(TTASR_E_NOMEM, "encoder_forward: workspace %zu < required %zu bytes", workspace_bytes, ws.total);
   if (reinterpret_cast<uintptr_t>(workspace_dev) & 1023) return fail(TTASR_E_ARG, "encoder_forward: workspace must be 1024-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
@@ -548,6 +610,11 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
   __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(wsb + ws.h);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(wsb + ws.qkv);
   __nv_bfloat16* ffn = reinterpret_cast<__nv_bfloat16*>(wsb + ws.ffn);
+  const bool fuse = h->fuse_ln;
+  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(wsb + ws.xb);   // bf16 copy of x (LayerNorm-fused mode)
+  void* st0 = wsb + ws.st0;   // LayerNorm partials of x as the attention block sees it (LN1)
+  void* st1 = wsb + ws.st1;   // ... as the MLP block sees it (LN2)
+  int parts0 = 0, parts1 = 0;
   const int d = c.d_model, f = c.ffn_dim, T = c.n_ctx, Tin = 2 * c.n_ctx;
   const int B = static_cast<int>(batch);
   const char* why = nullptr;
@@ -607,20 +674,24 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
     g.a = c1; g.lda = d; g.a_inner = d; g.rows = T; g.nbatch = B;
     g.w = h->conv2_w; g.n = d; g.kb_per_tap = d / 64; g.k_blocks = 3 * g.kb_per_tap;
     g.bias = h->conv2_b; g.act = 1; g.addend = h->pos; g.addend_bcast = 1; g.out = x; g.out_f32 = 1;
+    if (fuse) { g.ln_xb = xb; g.ln_stats_out = st0; g.ln_parts_out = &parts0; }
     GEMM_TRY(g, "conv2", kProfConv2);
   }
   const long long M = static_cast<long long>(B) * T;
   for (int i = 0; i < c.n_layers; ++i) {
     const LayerDev& l = h->layers[i];
-    prof_begin(kProfLayerNorm);
-    e = layernorm_launch(x, l.ln1_g, l.ln1_b, hbuf, M, d, 0, stream);
-    prof_end();
-    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d ln1: %s", i, cudaGetErrorString(e));
+    if (!fuse) {
+      prof_begin(kProfLayerNorm);
+      e = layernorm_launch(x, l.ln1_g, l.ln1_b, hbuf, M, d, 0, stream);
+      prof_end();
+      if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d ln1: %s", i, cudaGetErrorString(e));
+    }
     {
       GemmCall g;
-      g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
+      g.a = fuse ? xb : hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.wqkv; g.n = 3 * d; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.bqkv; g.out = qkv;
+      if (fuse) { g.ln_stats_in = st0; g.ln_parts_in = parts0; g.ln_c1 = l.c1_qkv; }
       GEMM_TRY(g, "qkv", kProfQkv);
     }
     prof_begin(kProfAttention);
@@ -632,17 +703,21 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
       g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.wo; g.n = d; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.bo; g.addend = x; g.out = x; g.out_f32 = 1;
+      if (fuse) { g.ln_xb = xb; g.ln_stats_out = st1; g.ln_parts_out = &parts1; }
       GEMM_TRY(g, "out_proj", kProfOutProj);
     }
-    prof_begin(kProfLayerNorm);
-    e = layernorm_launch(x, l.ln2_g, l.ln2_b, hbuf, M, d, 0, stream);
-    prof_end();
-    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d ln2: %s", i, cudaGetErrorString(e));
+    if (!fuse) {
+      prof_begin(kProfLayerNorm);
+      e = layernorm_launch(x, l.ln2_g, l.ln2_b, hbuf, M, d, 0, stream);
+      prof_end();
+      if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: layer %d ln2: %s", i, cudaGetErrorString(e));
+    }
     {
       GemmCall g;
-      g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
+      g.a = fuse ? xb : hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.w1; g.n = f; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.b1; g.act = 1; g.out = ffn;
+      if (fuse) { g.ln_stats_in = st1; g.ln_parts_in = parts1; g.ln_c1 = l.c1_fc1; }
       GEMM_TRY(g, "fc1", kProfFc1);
     }
     {
@@ -650,6 +725,7 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
       g.a = ffn; g.lda = f; g.a_inner = f; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.w2; g.n = d; g.k_blocks = f / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.b2; g.addend = x; g.out = x; g.out_f32 = 1;
+      if (fuse && i + 1 < c.n_layers) { g.ln_xb = xb; g.ln_stats_out = st0; g.ln_parts_out = &parts0; }
       GEMM_TRY(g, "fc2", kProfFc2);
     }
   }

@@ -303,3 +303,27 @@ def test_graph_buckets_survive_workspace_growth(cuda_device):
     torch.empty(64 << 20, dtype=torch.uint8, device=cuda_device).fill_(0xAB)   # scribble over whatever was freed
     again = graphed.encode([row])
     assert torch.equal(first, again)
+
+
+@pytest.mark.parametrize("arch_name", ["micro", "tiny"])
+def test_layernorm_fused_mode_matches_oracle(cuda_device, arch_name, monkeypatch):
+    """Opt-in TTASR_FUSE_LN=1: the per-layer LayerNorms are folded into the QKV / fc1 GEMMs (statistics and a bf16 copy
+    of the residual stream emitted by the residual GEMMs' epilogues).  Same tolerance as the default path, and the
+    two paths agree with each other far inside it."""
+    import torch
+
+    arch, w, enc_plain = _build(arch_name)
+    monkeypatch.setenv("TTASR_FUSE_LN", "1")
+    _, _, enc_fused = _build(arch_name)
+    monkeypatch.delenv("TTASR_FUSE_LN")
+    assert enc_fused.launches_per_forward == enc_plain.launches_per_forward - 2 * arch.layers
+    feats = np.stack([OF.log_mel(OF.synth_noise(31), arch.n_mels), OF.log_mel(OF.synth_tones(32), arch.n_mels),
+                      OF.log_mel(OF.pad_or_trim(OF.synth_short()), arch.n_mels)])
+    ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
+    got = enc_fused.encode(feats, out_dtype=torch.float32)
+    _check(got.cpu().numpy(), ref)
+    plain = enc_plain.encode(feats, out_dtype=torch.float32)
+    s = OE.parity_stats(got.cpu(), plain.cpu())
+    assert s["max_abs"] <= 0.05 and s["cosine"] >= 0.99995, s
+    assert torch.equal(got, enc_fused.encode(feats, out_dtype=torch.float32))      # deterministic
+    assert torch.equal(got[1], enc_fused.encode(feats[1:2], out_dtype=torch.float32)[0])  # batch-invariant
