@@ -327,3 +327,36 @@ def test_layernorm_fused_mode_matches_oracle(cuda_device, arch_name, monkeypatch
     assert s["max_abs"] <= 0.05 and s["cosine"] >= 0.99995, s
     assert torch.equal(got, enc_fused.encode(feats, out_dtype=torch.float32))      # deterministic
     assert torch.equal(got[1], enc_fused.encode(feats[1:2], out_dtype=torch.float32)[0])  # batch-invariant
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_residual_stream_with_outlier_channels_and_offset(cuda_device, fused, monkeypatch):
+    """Pre-trained Whisper encoders carry a few massive-activation channels and non-trivial LayerNorm gains; random
+    init has neither.  Emulate them: two positional channels pinned at +40 / -25, a +1.5 offset on every channel (a
+    token mean larger than the token's ordinary spread), LayerNorm gains in [0.5, 2] and biases ~0.3.  Both the
+    default path and the LayerNorm-fused one must stay inside the stated tolerance against the fp32 oracle."""
+    import torch
+    from ttasr import B200WhisperEncoder
+
+    arch = OE.ARCHS["tiny"]
+    w = OE.init_weights(arch, seed=3, std=0.05, ln_jitter=0.02)
+    g = torch.Generator().manual_seed(9)
+    pos = w["embed_positions.weight"].clone()
+    pos += 1.5
+    pos[:, 5] = 40.0
+    pos[:, 77] = -25.0
+    w["embed_positions.weight"] = pos
+    for k in list(w):
+        if k.endswith("layer_norm.weight"):
+            w[k] = 0.5 + 1.5 * torch.rand(arch.d_model, generator=g)
+        elif k.endswith("layer_norm.bias"):
+            w[k] = 0.3 * torch.randn(arch.d_model, generator=g)
+    w = OE.round_weights_bf16(w)
+    if fused:
+        monkeypatch.setenv("TTASR_FUSE_LN", "1")
+    enc = B200WhisperEncoder(_cfg(arch), w)
+    feats = np.stack([OF.log_mel(OF.synth_noise(41), arch.n_mels), OF.log_mel(OF.synth_tones(42), arch.n_mels)])
+    ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
+    got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
+    s = _check(got, ref)
+    print(f"outlier/offset stream, fused={fused}: {s}")
