@@ -19,6 +19,8 @@ GROUPS = [
     ("attention", ["tests/test_gpu_ops.py", "-k", "attention"]),
     ("bad_args", ["tests/test_gpu_ops.py", "-k", "bad_arguments"]),
     ("encoder", ["tests/test_gpu_encoder.py"]),
+    ("ingest", ["tests/test_ingest.py"]),
+    ("decode_handoff", ["tests/test_decode_handoff.py"]),
 ]
 
 
