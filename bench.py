@@ -146,20 +146,28 @@ def run_reference(args):
     if rank != 0:
         return 0
     ref = CpuReference(args.workload)
-    per_step = args.ref_chunks
+    # one warm-up pass pages in the weights / spins up the threads and tells how long a chunk takes here; the step is
+    # then sized (2..8 chunks) so that the whole --steps run stays within ~2.5 minutes on this box's cores
+    warm = synth_pcm_cpu(2)
+    ref.step(warm[:1])
+    t_chunk = ref.step(warm) / 2.0
+    per_step = args.ref_chunks if args.ref_chunks > 0 else int(max(2, min(8, 150.0 / max(args.steps, 1) / max(t_chunk, 1e-3))))
     pcm = synth_pcm_cpu(per_step)
-    for _ in range(max(1, min(args.warmup, 1))):  # one warm-up pass is enough to page in weights / spin up threads
-        ref.step(pcm)
     times = [ref.step(pcm) for _ in range(args.steps)]
     total = sum(times)
     value = per_step * CHUNK_SECONDS * args.steps / total
-    sample = (f"{per_step} x 30 s chunk(s) per step, {args.steps} steps; HF numpy log-mel + "
-              f"{'HF' if ref.kind == 'reference' else 'oracle-port'} fp32 encoder on CPU (CTranslate2 not installable)")
+    sample = (f"{per_step} x 30 s chunk(s) per step (a bounded sample of config.workload, NOT its "
+              f"{args.batch} chunks per step), {args.steps} steps; HF numpy log-mel + "
+              f"{'HF' if ref.kind == 'reference' else 'oracle-port'} fp32 encoder on {ref.cores} CPU threads "
+              "(the reference's CTranslate2 int8 CPU encoder is not installable offline)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, per_gpu_batch=args.batch),
+        "reference_step": {"chunks_per_step": per_step, "same_units_as_config": True,
+                           "note": "config names the workload both arms are quoted on; this arm times a bounded sample "
+                                   "of it per step (audio-s/s is per chunk, so the ratio is unit-consistent)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": ref.kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -227,8 +235,9 @@ class ClockSampler:
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20", "-i",
                  str(gpu_index)], stdout=self.fh, stderr=subprocess.DEVNULL)
+            time.sleep(0.3)   # nvidia-smi needs a moment before its first sample
         except Exception:
             self.proc = None
 
@@ -265,6 +274,65 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def library_baseline(cfg, weights, pcm, dev, our_value, our_frontend):
+    """Informational: the same work done by LIBRARY kernels on the same B200 in the same process (SURVEY.md 2d's honest
+    baseline) — Hugging Face WhisperEncoder in bf16 with SDPA attention (cuBLAS GEMMs, cuDNN/flash attention, eager
+    LayerNorm/GELU) and torch.stft + matmul for the log-mel front end (the HF torch extractor's arithmetic, a4).
+    Not the reference arm and not a target; it only turns "hand-written beats the libraries by X" into a number."""
+    import torch
+    from transformers import WhisperConfig
+    from transformers.models.whisper.modeling_whisper import WhisperEncoder
+
+    from ttasr.mel import slaney_mel_filters
+
+    hcfg = WhisperConfig(d_model=cfg.d_model, encoder_layers=cfg.encoder_layers,
+                         encoder_attention_heads=cfg.encoder_attention_heads, encoder_ffn_dim=cfg.encoder_ffn_dim,
+                         num_mel_bins=cfg.num_mel_bins, decoder_layers=1, decoder_attention_heads=cfg.encoder_attention_heads,
+                         decoder_ffn_dim=64, max_source_positions=cfg.max_source_positions, attn_implementation="sdpa")
+    with torch.device(dev):
+        hf = WhisperEncoder(hcfg).eval().to(torch.bfloat16)
+    hf.load_state_dict({k: v.to(torch.bfloat16) for k, v in weights.items()}, strict=True)
+    Bl = min(64, pcm.shape[0])
+    window = torch.hann_window(400, device=dev)
+    fb = torch.from_numpy(slaney_mel_filters(cfg.num_mel_bins).astype("float32")).to(dev)   # [201, n_mels]
+
+    def torch_logmel(x):
+        st = torch.stft(x, 400, 160, window=window, return_complex=True)
+        mel = fb.T @ (st[..., :-1].abs() ** 2)
+        lg = torch.clamp(mel, min=1e-10).log10()
+        lg = torch.maximum(lg, lg.amax(dim=(1, 2), keepdim=True) - 8.0)
+        return (lg + 4.0) / 4.0
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    with torch.no_grad():
+        for _ in range(2):
+            f = torch_logmel(pcm[:Bl])
+            hf(f.to(torch.bfloat16))
+        torch.cuda.synchronize()
+        a, b, c = ev(), ev(), ev()
+        n = 3
+        fe_ms = enc_ms = 0.0
+        for _ in range(n):
+            a.record()
+            f = torch_logmel(pcm[:Bl])
+            b.record()
+            hf(f.to(torch.bfloat16))
+            c.record()
+            torch.cuda.synchronize()
+            fe_ms += a.elapsed_time(b)
+            enc_ms += b.elapsed_time(c)
+    lib_value = Bl * CHUNK_SECONDS * n / ((fe_ms + enc_ms) / 1e3)
+    fe_bytes = Bl * (N_SAMPLES * 4 + cfg.num_mel_bins * 3000 * 4)
+    return {"what": "HF WhisperEncoder bf16 + SDPA (cuBLAS / cuDNN / eager elementwise) and torch.stft log-mel, same GPU, "
+                    f"same weights, {Bl} chunks per step, {n} steps after 2 warm-ups",
+            "value": lib_value, "unit": UNIT, "ours_over_library": our_value / lib_value,
+            "encoder_ms_per_chunk": enc_ms / n / Bl, "frontend_ms_per_chunk": fe_ms / n / Bl,
+            "frontend_gbs": fe_bytes / (fe_ms / n) / 1e6,
+            "frontend_ours_over_library": our_frontend["achieved"] / (fe_bytes / (fe_ms / n) / 1e6)}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -288,7 +356,8 @@ def run_ours(args):
     cfg = arch_table(args.workload)
     B = args.batch
     fe = ttasr.B200WhisperFeatureExtractor(feature_size=cfg.num_mel_bins)
-    enc = ttasr.B200WhisperEncoder(cfg, make_gpu_weights(cfg, dev, seed=0))
+    weights = make_gpu_weights(cfg, dev, seed=0)
+    enc = ttasr.B200WhisperEncoder(cfg, weights, residual=args.residual)
     torch.cuda.empty_cache()
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     pcm = (0.1 * torch.randn((B, N_SAMPLES), generator=g, device=dev)).clamp_(-1, 1)
@@ -321,6 +390,8 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    last_local_ms = [0.0]
+
     def timed(fn, steps, **kw):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -330,7 +401,13 @@ def run_ours(args):
             out = fn(**kw)
         e1.record()
         barrier()
-        return all_max(e0.elapsed_time(e1)), out
+        last_local_ms[0] = e0.elapsed_time(e1)
+        return all_max(last_local_ms[0]), out
+
+    # ---- cross-rank determinism probe: the same seeded chunks must give the same bits on every rank
+    from ttasr.dp import gather_host, probe_digest
+
+    probe_sha, probe_same = probe_digest(ttasr.B200LogMelEncoder(fe, enc))
 
     # ---- device-resident arm
     for _ in range(args.warmup):
@@ -338,9 +415,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     enc.profile(True)
     enc.profile_read(reset=True)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local)
     ms_total, out = timed(step_device, args.steps, record_fe=True)
-    clocks = sampler.stop() if sampler else None
+    clocks = sampler.stop()
+    per_rank = gather_host({"rank": rank, "ms_per_step": last_local_ms[0] / args.steps, "sm_mhz": clocks.get("sm_mhz"),
+                            "power_w_max": clocks.get("power_w_max"), "reasons": clocks.get("reasons")})
     stages = enc.profile_read(reset=True)
     enc.profile(False)
     fe_ms = [a.elapsed_time(b) for a, b in fe_events]
@@ -448,7 +527,16 @@ def run_ours(args):
         "clocks": clocks, "roofline": roofline, "gemm_roofline": gemm_roofline, "frontend_roofline": frontend,
         "encoder_tflops_whole_step": enc_flops / (ms_total / 1e3) / 1e12 / n_gpus,
         "kernels": kernels,
+        "residual_stream": enc.residual or os.environ.get("TTASR_RESIDUAL") or "split (library default)",
+        "rank_probe": {"sha256": probe_sha, "identical_on_all_ranks": bool(probe_same), "ranks": n_gpus,
+                       "what": "3 seeded probe chunks encoded on every rank before the timed region (ttasr.dp.probe_digest)"},
+        "per_rank": per_rank,
     }
+    if n_gpus == 1 and not args.no_library_baseline:
+        try:
+            line["gpu_library_baseline"] = library_baseline(cfg, weights, pcm, dev, value, frontend)
+        except Exception as exc:  # informational only: never fail the bench line over it
+            line["gpu_library_baseline"] = {"unavailable": f"{type(exc).__name__}: {exc}"[:200]}
     if n_gpus == 1 and not args.no_cpu_baseline:
         ref = CpuReference(args.workload)
         sample_pcm = host_pcm[: args.ref_chunks].numpy()
@@ -473,7 +561,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="large-v3", choices=["tiny", "base", "small", "medium", "large-v2", "large-v3"])
     ap.add_argument("--batch", type=int, default=256, help="30 s chunks per GPU per step")
-    ap.add_argument("--ref-chunks", type=int, default=2, help="chunks per CPU reference step / cpu_baseline sample")
+    ap.add_argument("--ref-chunks", type=int, default=0,
+                    help="chunks per CPU reference step (0 = sized from a warm-up pass: 2..8) / cpu_baseline sample")
+    ap.add_argument("--residual", default=None, choices=["split", "f32", "bf16"],
+                    help="residual-stream representation of the encoder (default: the library's, see ttasr_abi.h)")
+    ap.add_argument("--no-library-baseline", action="store_true",
+                    help="skip the informational HF bf16 + SDPA / torch.stft comparison on the same GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -133,9 +133,23 @@ typedef struct {
   const ttasr_layer_weights* layers;                /* host array, n_layers entries */
 } ttasr_weights;
 
+/* How the residual stream x is held between the encoder blocks.
+ *   TTASR_RESIDUAL_SPLIT (library default): x = hi + lo, two bf16 arrays (16 mantissa bits, the HBM cost of one fp32
+ *     array).  `hi` is itself the bf16 A operand of the QKV / fc1 projections: the per-layer LayerNorms
+ *     (modeling_whisper.py:393,403) are folded into those GEMMs (gamma into the weights, mean / rstd applied in the
+ *     epilogue from row statistics the residual GEMMs emit), so no LayerNorm kernel runs between the blocks.
+ *   TTASR_RESIDUAL_F32: fp32 array and one LayerNorm kernel in front of each QKV / fc1 GEMM (normalises before the
+ *     bf16 rounding; the reference-precision path, ~5 % slower).
+ *   TTASR_RESIDUAL_BF16: `hi` only — what an all-bf16 Hugging Face run keeps; measured in DESIGN.md, not recommended.
+ *   TTASR_RESIDUAL_AUTO: the environment (TTASR_RESIDUAL=f32|split|bf16) or else the library default. */
+enum { TTASR_RESIDUAL_AUTO = -1, TTASR_RESIDUAL_F32 = 0, TTASR_RESIDUAL_SPLIT = 1, TTASR_RESIDUAL_BF16 = 2 };
+
 /* Packs the weights into its own device buffers (fused QKV with the d_h^-1/2 query scale folded in, conv filters
  * tap-major), builds TMA descriptors.  The caller may free its weight tensors afterwards. */
 TTASR_API int ttasr_encoder_create(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, ttasr_encoder_t** out);
+/* ttasr_encoder_create with an explicit residual-stream representation (ttasr_encoder_create = TTASR_RESIDUAL_AUTO) */
+TTASR_API int ttasr_encoder_create_ex(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, int residual,
+                                      ttasr_encoder_t** out);
 TTASR_API int ttasr_encoder_workspace_bytes(const ttasr_encoder_t* h, int64_t batch, size_t* out);
 /* feats: layout per `feats_layout` (tmajor_ld only read for the bf16 layout).  workspace_dev: >= workspace_bytes,
  * 1024-byte aligned.  out_dev: [batch, n_ctx, d_model] bf16 or fp32 per `out_dtype` (last_hidden_state). */
@@ -162,6 +176,29 @@ TTASR_API void ttasr_encoder_destroy(ttasr_encoder_t* h);
  *        out_dtype TTASR_OUT_*; cta_group 1 or 2 (CTA-pair MMA), 0 = library default. */
 TTASR_API int ttasr_op_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, const float* addend_dev, void* out_dev,
                   int64_t M, int64_t N, int64_t K, int act, int out_dtype, int cta_group, void* stream);
+/* gemm_split: the residual GEMM on the split stream (TTASR_RESIDUAL_SPLIT):
+ *        (outh, outl) = split(act(a[M, K] * w[N, K]^T + bias[N]) + (addh[M, N] + addl[M, N])), all bf16; split(x) =
+ *        (bf16(x), bf16(x - bf16(x))); outl and addl may both be NULL (plain bf16 stream); add* may alias out*.
+ *        stats_out: optional float2 [M, N / 64]: per row and per 64 columns the (mean, sum of squared deviations) of
+ *        the new outh values — what ttasr_op_gemm_lnfold consumes.  N % 128 == 0. */
+TTASR_API int ttasr_op_gemm_split(const void* a_dev, const void* w_dev, const float* bias_dev, const void* addh_dev,
+                                  const void* addl_dev, void* outh_dev, void* outl_dev, void* stats_out_dev, int64_t M,
+                                  int64_t N, int64_t K, int act, int cta_group, void* stream);
+/* gemm_lnfold: out[M, N] bf16 = act(LayerNorm(a)[M, K] * W^T + b) computed on the UN-normalised bf16 rows `a`:
+ *        w_dev = bf16(W * gamma) [N, K], c1[n] = sum_k w_dev[n, k], c2[n] = b[n] + sum_k beta[k] W[n, k] (fp32), and
+ *        out = act(rstd * (a w_dev^T - mean * c1) + c2) with mean / rstd per row combined from stats_in
+ *        (float2 [M, parts] partial (mean, M2) over K / parts columns each, as written by ttasr_op_gemm_split). */
+TTASR_API int ttasr_op_gemm_lnfold(const void* a_dev, const void* w_dev, const float* c1_dev, const float* c2_dev,
+                                   const void* stats_in_dev, int parts, void* out_dev, int64_t M, int64_t N, int64_t K,
+                                   int act, float eps, int cta_group, void* stream);
+/* conv_stem: the encoder's two-layer convolutional stem on its own (modeling_whisper.py:567-568,619-626):
+ *        feats_tm [B, 2T, ld] bf16 time-major (channels >= n_mels are ignored) -> GELU(conv1, k=3, p=1) ->
+ *        GELU(conv2, k=3, s=2, p=1) + pos[T, d] -> out [B, T, d] fp32.  Weights in the HF layout: conv1_w
+ *        [d, n_mels, 3], conv2_w [d, d, 3] bf16; biases and pos fp32.  scratch_dev: [B, 2T, d] bf16. */
+TTASR_API int ttasr_op_conv_stem(const void* feats_tm_dev, int ld, int n_mels, int64_t B, int T, int d,
+                                 const void* conv1_w_dev, const float* conv1_b_dev, const void* conv2_w_dev,
+                                 const float* conv2_b_dev, const float* pos_dev, void* scratch_dev, float* out_dev,
+                                 void* stream);
 /* layernorm: y[rows, d] = (x - mean) / sqrt(var + 1e-5) * g + b, x fp32, y per out_dtype */
 TTASR_API int ttasr_op_layernorm(const float* x_dev, const float* g_dev, const float* b_dev, void* y_dev, int64_t rows, int d,
                        int out_dtype, void* stream);

@@ -16,7 +16,19 @@
 //   warps 4-11 epilogue    : two warpgroups taking alternate column slabs: tcgen05.ld -> bias / GELU / + addend ->
 //                            swizzled st.shared; they only ever wait on mbarriers, never on TMA bookkeeping
 // Tiles are walked n-fastest so the CTAs of a wave share a few A row-blocks and all of W in L2.
+//
+// Epilogue flavours (template parameter EPI):
+//   kEpiBf16    out bf16 = act(acc + bias); optionally with a LayerNorm folded in (see GemmCall::ln_stats_in)
+//   kEpiF32     out fp32 = act(acc + bias)
+//   kEpiF32Add  out fp32 = act(acc + bias) + fp32 addend                  (fp32 residual stream, TTASR_FUSE_LN=0)
+//   kEpiSplit   (out_hi, out_lo) bf16 pair = split(act(acc + bias) + (add_hi + add_lo)), plus per-row partial
+//               LayerNorm statistics of out_hi                             (split residual stream, the default)
 #include "gemm_sm100.h"
+
+#include <string.h>
+
+#include <unordered_map>
+
 #include "ptx_sm100.cuh"
 
 namespace ttasr {
@@ -30,14 +42,18 @@ constexpr int kSlabBytes = kBM * 128;  // staging slab: 128 rows x 128 B
 constexpr int kThreadsGemm = 384;
 constexpr int kMaxSmem = 232448;  // 227 KB
 
-template <int BN, int CG, bool HAS_ADD>
+enum { kEpiBf16 = 0, kEpiF32 = 1, kEpiF32Add = 2, kEpiSplit = 3 };
+
+template <int BN, int CG, int EPI>
 struct Cfg {
   static constexpr int kABytes = kBM * kBK * 2;
   static constexpr int kBRows = BN / CG;
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  // staging ring: deeper for the addend variants (each slab is in flight from its TMA prefetch until its store is read)
-  static constexpr int kNBuf = 4;
+  // staging ring of 16 KB slabs (each slab is in flight from its TMA prefetch / first write until its store is read).
+  // The split epilogue moves slabs in (hi, lo) PAIRS: kNPair pairs = 2 * kNPair buffers.
+  static constexpr int kNPair = (BN == 256 && CG == 1) ? 2 : 3;
+  static constexpr int kNBuf = (EPI == kEpiSplit) ? 2 * kNPair : 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kStagesRaw = (kMaxSmem - 1024 - kBarBytes - kNBuf * kSlabBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -52,6 +68,8 @@ struct GemmParams {
   CUtensorMap tm_w;    // 2-D (k, n)
   CUtensorMap tm_out;  // 3-D (n, row, batch)
   CUtensorMap tm_add;  // 3-D (n, row, batch|1)
+  CUtensorMap tm_out2; // split epilogue: the lo half of the output pair
+  CUtensorMap tm_add2; // split epilogue: the lo half of the addend pair
   const float* bias;
   int mode;
   int k_blocks;
@@ -60,12 +78,13 @@ struct GemmParams {
   int tiles_n;
   int num_tiles;
   int add_bcast;
-  // ---- optional LayerNorm fusion (see GemmCall)
-  __nv_bfloat16* ln_xb;        // producer side: bf16 copy of the fp32 output rows
-  float2* ln_stats_out;        // producer side: per-row partial (sum, sum of squares): [row][2 * tiles_n]
+  // ---- LayerNorm fusion (see GemmCall)
+  int has_lo;                  // split epilogue: the lo halves exist (0 = plain bf16 residual stream)
+  float2* ln_stats_out;        // producer side: per-row partial (mean, M2) of each 64-column slab: [row][n / 64]
   const float2* ln_stats_in;   // consumer side: partials of the A operand's rows: [row][ln_parts_in]
   const float* ln_c1;          // consumer side: [n] column sums of the gamma-folded weights
   int ln_parts_in;
+  float ln_part_n;             // columns behind each partial
   float ln_inv_k;              // 1 / (normalised width)
   float ln_eps;
   int rows;                    // output rows per batch item
@@ -91,15 +110,24 @@ __device__ __forceinline__ float apply_act(float x) {
   return x;
 }
 
-template <int BN, int CG, int ACT, bool HAS_ADD, bool OUT_F32>
+// bf16 pair word -> two fp32 (exact)
+__device__ __forceinline__ void bf16x2_to_f32(uint32_t w, float& lo, float& hi) {
+  lo = __uint_as_float(w << 16);
+  hi = __uint_as_float(w & 0xffff0000u);
+}
+
+template <int BN, int CG, int ACT, int EPI>
 __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_constant__ GemmParams p) {
-  using C = Cfg<BN, CG, HAS_ADD>;
+  using C = Cfg<BN, CG, EPI>;
+  constexpr bool OUT_F32 = (EPI == kEpiF32 || EPI == kEpiF32Add);
+  constexpr bool HAS_ADD = (EPI == kEpiF32Add);
+  constexpr bool SPLIT = (EPI == kEpiSplit);
   constexpr int kStages = C::kStages;
   constexpr int kNBuf = C::kNBuf;
+  constexpr int kRing = SPLIT ? C::kNPair : kNBuf;   // entries of the staging ring (slabs, or slab pairs)
   constexpr int kSlabCols = OUT_F32 ? 32 : 64;
   constexpr int kNSlab = BN / kSlabCols;
   static_assert(kNSlab % 2 == 0, "two epilogue warpgroups take alternate slabs");
-  static_assert(OUT_F32 || !HAS_ADD, "bf16 output with an addend is not instantiated");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = smem_u32(smem_raw);
@@ -117,6 +145,8 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
   auto buf_free = [&](int i) { return sBar + 8u * (2 * kStages + 4 + 2 * kNBuf + i); };
   const uint32_t tmem_slot = sBar + 8u * (2 * kStages + 4 + 3 * kNBuf);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem0));
+  // staging address of ring entry e (split: the hi slab; the lo slab follows it)
+  auto slab_addr = [&](uint32_t e) { return sE + e * (SPLIT ? 2u : 1u) * kSlabBytes; };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,7 +158,11 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
     prefetch_tmap(&p.tm_a);
     prefetch_tmap(&p.tm_w);
     prefetch_tmap(&p.tm_out);
-    if (HAS_ADD) prefetch_tmap(&p.tm_add);
+    if (HAS_ADD || SPLIT) prefetch_tmap(&p.tm_add);
+    if (SPLIT) {
+      prefetch_tmap(&p.tm_out2);
+      prefetch_tmap(&p.tm_add2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -229,18 +263,19 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
   } else if (warp == 2) {
     // ===================================================== output-store thread
     if (lane == 0) {
-      uint32_t q = 0;  // running slab counter -> staging buffer q % kNBuf, use number q / kNBuf
+      uint32_t q = 0;  // running slab counter -> ring entry q % kRing, use number q / kRing
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
         int b, t0, n0;
         tile_coords(tile, b, t0, n0);
         for (int s = 0; s < kNSlab; ++s, ++q) {
-          const uint32_t buf = q % kNBuf;
-          mbar_wait(out_ready(buf), (q / kNBuf) & 1);
-          tma_store_3d(&p.tm_out, sE + buf * kSlabBytes, n0 + s * kSlabCols, t0, b);
+          const uint32_t e = q % kRing;
+          mbar_wait(out_ready(e), (q / kRing) & 1);
+          tma_store_3d(&p.tm_out, slab_addr(e), n0 + s * kSlabCols, t0, b);
+          if (SPLIT && p.has_lo) tma_store_3d(&p.tm_out2, slab_addr(e) + kSlabBytes, n0 + s * kSlabCols, t0, b);
           tma_store_commit();
-          if (q > 0) {  // the previous store has finished reading its slab: recycle it
+          if (q > 0) {  // the previous store has finished reading its slab(s): recycle them
             tma_store_wait_read<1>();
-            mbar_arrive(buf_free((q - 1) % kNBuf));
+            mbar_arrive(buf_free((q - 1) % kRing));
           }
         }
       }
@@ -248,17 +283,23 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
     }
   } else if (warp == 3) {
     // ===================================================== addend loader
-    if (HAS_ADD && lane == 0) {
+    if ((HAS_ADD || SPLIT) && lane == 0) {
       uint32_t q = 0;
       for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
         int b, t0, n0;
         tile_coords(tile, b, t0, n0);
         const int add_b = p.add_bcast ? 0 : b;
         for (int s = 0; s < kNSlab; ++s, ++q) {
-          const uint32_t buf = q % kNBuf;
-          mbar_wait(buf_free(buf), ((q / kNBuf) & 1) ^ 1);
-          mbar_arrive_expect_tx(add_full(buf), kSlabBytes);
-          tma_load_3d(sE + buf * kSlabBytes, &p.tm_add, add_full(buf), n0 + s * kSlabCols, t0, add_b);
+          const uint32_t e = q % kRing;
+          mbar_wait(buf_free(e), ((q / kRing) & 1) ^ 1);
+          if constexpr (SPLIT) {
+            mbar_arrive_expect_tx(add_full(e), p.has_lo ? 2 * kSlabBytes : kSlabBytes);
+            tma_load_3d(slab_addr(e), &p.tm_add, add_full(e), n0 + s * kSlabCols, t0, add_b);
+            if (p.has_lo) tma_load_3d(slab_addr(e) + kSlabBytes, &p.tm_add2, add_full(e), n0 + s * kSlabCols, t0, add_b);
+          } else {
+            mbar_arrive_expect_tx(add_full(e), kSlabBytes);
+            tma_load_3d(slab_addr(e), &p.tm_add, add_full(e), n0 + s * kSlabCols, t0, add_b);
+          }
         }
       }
     }
@@ -282,33 +323,41 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
       // ---- LayerNorm fusion, per tile: this thread owns output row (b, t0 + row)
       const bool row_ok = (t0 + row) < p.rows;
       const long long grow = static_cast<long long>(b) * p.rows + t0 + row;
-      const bool ln_emit = OUT_F32 && (p.ln_stats_out != nullptr);
-      float ln_s1 = 0.f, ln_s2 = 0.f;
-      __nv_bfloat16* ln_xb_row = ln_emit ? p.ln_xb + grow * p.n : nullptr;
       float ln_a = 1.f, ln_b = 0.f;      // consumer side: out = ln_a * acc + ln_b * c1[n] + c2[n]
-      const bool ln_in = !OUT_F32 && (p.ln_stats_in != nullptr);
+      const bool ln_in = (EPI == kEpiBf16) && (p.ln_stats_in != nullptr);
       if (ln_in) {
-        float s1 = 0.f, s2 = 0.f;
+        // combine the partial (mean_i, M2_i) pairs (equal counts) in a fixed order: bit-reproducible statistics
+        float mean = 0.f, m2 = 0.f;
         if (row_ok) {
           const float2* st = p.ln_stats_in + grow * p.ln_parts_in;
-          for (int i = 0; i < p.ln_parts_in; ++i) {  // fixed order: bit-reproducible statistics
+          float msum = 0.f;
+          for (int i = 0; i < p.ln_parts_in; ++i) msum += __ldg(st + i).x;
+          mean = msum / static_cast<float>(p.ln_parts_in);
+          float dev2 = 0.f;
+          for (int i = 0; i < p.ln_parts_in; ++i) {
             const float2 t = __ldg(st + i);
-            s1 += t.x;
-            s2 += t.y;
+            const float dm = t.x - mean;
+            dev2 = fmaf(dm, dm, dev2);
+            m2 += t.y;
           }
+          m2 = fmaf(p.ln_part_n, dev2, m2);
         }
-        const float mean = s1 * p.ln_inv_k;
-        const float var = fmaxf(fmaf(s2, p.ln_inv_k, -mean * mean), 0.f);
+        const float var = fmaxf(m2 * p.ln_inv_k, 0.f);
         ln_a = rsqrtf(var + p.ln_eps);
         ln_b = -ln_a * mean;
       }
 #pragma unroll 1
       for (int s = wg; s < kNSlab; s += 2) {
         const uint32_t q = q0 + s;
-        const uint32_t buf = q % kNBuf;
-        const uint32_t use = (q / kNBuf) & 1;
-        const uint32_t slab = sE + buf * kSlabBytes;
+        const uint32_t e = q % kRing;
+        const uint32_t use = (q / kRing) & 1;
+        const uint32_t slab = slab_addr(e);
         const bool last = (s + 2 >= kNSlab);
+        // producer side (split epilogue): sums of (v - K) and (v - K)^2 over this row's 64 hi values of the slab, K = the
+        // first of them (a shift inside the data's own range keeps the one-pass variance well conditioned).  One partial
+        // per 64 columns whatever the tile shape, so the statistics do not depend on the launcher's choice of BN / CG.
+        float st_k = 0.f;
+        f32x2_t st_s1 = pack2(0.f, 0.f), st_s2 = pack2(0.f, 0.f);
 
         if constexpr (OUT_F32) {
           uint32_t acc[32];
@@ -319,10 +368,9 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
           }
-          if (HAS_ADD) mbar_wait(add_full(buf), use);         // addend slab landed (prefetched by warp 3)
-          else mbar_wait(buf_free(buf), use ^ 1);             // slab recycled by the store thread
+          if (HAS_ADD) mbar_wait(add_full(e), use);         // addend slab landed (prefetched by warp 3)
+          else mbar_wait(buf_free(e), use ^ 1);             // slab recycled by the store thread
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 32);
-          uint32_t xbw[16];  // bf16 copy of this row's 32 columns (LayerNorm fusion only)
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const float4 bv = __ldg(bias4 + c);
@@ -351,17 +399,6 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
               }
             }
             sts128(addr, v);
-            if (ln_emit) {
-              ln_s1 += (v.x + v.y) + (v.z + v.w);
-              ln_s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, ln_s2))));
-              xbw[2 * c] = pack_bf16x2(v.x, v.y);
-              xbw[2 * c + 1] = pack_bf16x2(v.z, v.w);
-            }
-          }
-          if (ln_emit && row_ok) {
-            uint4* dst = reinterpret_cast<uint4*>(ln_xb_row + n0 + s * 32);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) dst[c] = make_uint4(xbw[4 * c], xbw[4 * c + 1], xbw[4 * c + 2], xbw[4 * c + 3]);
           }
         } else {
           uint32_t acc0[32], acc1[32];
@@ -373,7 +410,8 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
           }
-          mbar_wait(buf_free(buf), use ^ 1);
+          if (SPLIT) mbar_wait(add_full(e), use);           // addend (hi, lo) slabs landed (prefetched by warp 3)
+          else mbar_wait(buf_free(e), use ^ 1);
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 64);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 16-byte chunk = 8 bf16 columns
@@ -382,6 +420,54 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
             uint32_t aa[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) aa[i] = a[i];
+            if constexpr (SPLIT) {
+              // x' = act(acc + bias) + (add_hi + add_lo) in fp32; out_hi = bf16(x'), out_lo = bf16(x' - out_hi)
+              const uint32_t addr = slab + row_off + ((c ^ swz) << 4);
+              f32x2_t x[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const f32x2_t bb = (j == 0) ? pack2(b0.x, b0.y) : (j == 1) ? pack2(b0.z, b0.w) : (j == 2) ? pack2(b1.x, b1.y) : pack2(b1.z, b1.w);
+                x[j] = add2(pack2(__uint_as_float(aa[2 * j]), __uint_as_float(aa[2 * j + 1])), bb);
+                if constexpr (ACT == 1) x[j] = gelu_erf_f32x2(x[j]);
+              }
+              uint32_t h[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(addr));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float f0, f1;
+                bf16x2_to_f32(h[j], f0, f1);
+                x[j] = add2(x[j], pack2(f0, f1));
+              }
+              if (p.has_lo) {
+                uint32_t l[4];
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(addr + kSlabBytes));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  float f0, f1;
+                  bf16x2_to_f32(l[j], f0, f1);
+                  x[j] = add2(x[j], pack2(f0, f1));
+                }
+              }
+              uint32_t oh[4], ol[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float x0, x1, f0, f1;
+                unpack2(x[j], x0, x1);
+                oh[j] = pack_bf16x2(x0, x1);
+                bf16x2_to_f32(oh[j], f0, f1);
+                if (c == 0 && j == 0) st_k = f0;
+                const f32x2_t hv = pack2(f0, f1);
+                const f32x2_t dv = add2(hv, pack2(-st_k, -st_k));
+                st_s1 = add2(st_s1, dv);
+                st_s2 = fma2(dv, dv, st_s2);
+                float r0, r1;
+                unpack2(add2(x[j], pack2(-f0, -f1)), r0, r1);
+                ol[j] = pack_bf16x2(r0, r1);
+              }
+              sts128u(addr, oh[0], oh[1], oh[2], oh[3]);
+              if (p.has_lo) sts128u(addr + kSlabBytes, ol[0], ol[1], ol[2], ol[3]);
+              continue;
+            }
             if (ln_in) {  // LayerNorm folded in: x = ln_a * acc + (ln_b * c1 + c2); the code below then adds "bias" 0
               const float4* c14 = reinterpret_cast<const float4*>(p.ln_c1 + n0 + s * 64);
               const float4 k0 = __ldg(c14 + 2 * c), k1 = __ldg(c14 + 2 * c + 1);
@@ -428,10 +514,18 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
         }
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
         __syncwarp();
-        if (lane == 0) mbar_arrive(out_ready(buf));
+        if (lane == 0) mbar_arrive(out_ready(e));
+        if (SPLIT && p.ln_stats_out != nullptr && row_ok) {
+          // mean = K + s1 / 64, M2 = s2 - s1^2 / 64
+          float a0, a1, e0, e1;
+          unpack2(st_s1, a0, a1);
+          unpack2(st_s2, e0, e1);
+          const float s1 = a0 + a1, s2 = e0 + e1;
+          const float mean = fmaf(s1, 1.0f / 64.0f, st_k);
+          const float m2 = fmaxf(fmaf(-s1, s1 * (1.0f / 64.0f), s2), 0.f);
+          p.ln_stats_out[grow * (p.n >> 6) + ((n0 >> 6) + s)] = make_float2(mean, m2);
+        }
       }
-      if (ln_emit && row_ok)
-        p.ln_stats_out[grow * (2 * p.tiles_n) + (n0 / BN) * 2 + wg] = make_float2(ln_s1, ln_s2);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
@@ -458,10 +552,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int BN, int CG, int ACT, bool HAS_ADD, bool OUT_F32>
+template <int BN, int CG, int ACT, int EPI>
 cudaError_t launch_variant(const GemmParams& p, int num_sms, cudaStream_t stream) {
-  using C = Cfg<BN, CG, HAS_ADD>;
-  auto kern = gemm_kernel<BN, CG, ACT, HAS_ADD, OUT_F32>;
+  using C = Cfg<BN, CG, EPI>;
+  auto kern = gemm_kernel<BN, CG, ACT, EPI>;
   static PerDeviceOnce attr_done;
   if (attr_done.need()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
@@ -486,24 +580,60 @@ cudaError_t launch_variant(const GemmParams& p, int num_sms, cudaStream_t stream
 
 template <int BN, int CG>
 cudaError_t dispatch_epilogue(const GemmCall& c, const GemmParams& p, int num_sms, cudaStream_t stream) {
+  if (c.split) {
+    return c.act ? launch_variant<BN, CG, 1, kEpiSplit>(p, num_sms, stream)
+                 : launch_variant<BN, CG, 0, kEpiSplit>(p, num_sms, stream);
+  }
   if (c.out_f32) {
     if (c.addend) {
-      return c.act ? launch_variant<BN, CG, 1, true, true>(p, num_sms, stream)
-                   : launch_variant<BN, CG, 0, true, true>(p, num_sms, stream);
+      return c.act ? launch_variant<BN, CG, 1, kEpiF32Add>(p, num_sms, stream)
+                   : launch_variant<BN, CG, 0, kEpiF32Add>(p, num_sms, stream);
     }
-    return c.act ? launch_variant<BN, CG, 1, false, true>(p, num_sms, stream)
-                 : launch_variant<BN, CG, 0, false, true>(p, num_sms, stream);
+    return c.act ? launch_variant<BN, CG, 1, kEpiF32>(p, num_sms, stream)
+                 : launch_variant<BN, CG, 0, kEpiF32>(p, num_sms, stream);
   }
-  return c.act ? launch_variant<BN, CG, 1, false, false>(p, num_sms, stream)
-               : launch_variant<BN, CG, 0, false, false>(p, num_sms, stream);
+  return c.act ? launch_variant<BN, CG, 1, kEpiBf16>(p, num_sms, stream)
+               : launch_variant<BN, CG, 0, kEpiBf16>(p, num_sms, stream);
 }
 
+}  // namespace
+
+// cuTensorMapEncodeTiled costs ~1 us on the host and a forward issues several hundred of them with only a few dozen
+// DISTINCT (pointer, shape, box) combinations (the same workspace buffers every layer): memoise per thread.  A map is a
+// pure function of the key, so a recycled pointer with the same geometry yields the same (still valid) descriptor.
+namespace {
+struct TmapKey {
+  uint64_t v[14];
+  bool operator==(const TmapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9e3779b97f4a7c15ull;
+    for (uint64_t x : k.v) { h ^= x + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); }
+    return static_cast<size_t>(h);
+  }
+};
 }  // namespace
 
 CUresult encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* ptr, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return CUDA_ERROR_NOT_SUPPORTED;
+  if (rank < 1 || rank > 4) return CUDA_ERROR_INVALID_VALUE;
+  TmapKey key{};
+  key.v[0] = reinterpret_cast<uint64_t>(ptr);
+  key.v[1] = (static_cast<uint64_t>(dtype) << 32) | (static_cast<uint64_t>(rank) << 16) | static_cast<uint64_t>(swizzle);
+  for (int i = 0; i < rank; ++i) {
+    key.v[2 + i] = dims[i];
+    key.v[10 + i] = box[i];
+  }
+  for (int i = 0; i + 1 < rank; ++i) key.v[6 + i] = strides_bytes[i];
+  static thread_local std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *map = it->second;
+    return CUDA_SUCCESS;
+  }
   cuuint64_t gdim[5];
   cuuint64_t gstr[4];
   cuuint32_t bdim[5], estr[5];
@@ -513,9 +643,14 @@ CUresult encode_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, cons
     estr[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  return fn(map, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdim, gstr, bdim, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUresult r = fn(map, dtype, static_cast<cuuint32_t>(rank), const_cast<void*>(ptr), gdim, gstr, bdim, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_SUCCESS) {
+    if (cache.size() >= 4096) cache.clear();
+    cache.emplace(key, *map);
+  }
+  return r;
 }
 
 cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, const char** why) {
@@ -530,7 +665,21 @@ cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, con
     *why = "gemm: operands must be 16-byte aligned with 16-byte row pitch";
     return cudaErrorInvalidValue;
   }
-  if (c.addend && !c.out_f32) { *why = "gemm: addend requires fp32 output"; return cudaErrorInvalidValue; }
+  if (c.addend && (!c.out_f32 || c.split)) { *why = "gemm: an fp32 addend requires fp32 output"; return cudaErrorInvalidValue; }
+  if (c.split) {
+    if (c.out_f32 || !c.addend_hi || (c.out_lo == nullptr) != (c.addend_lo == nullptr)) {
+      *why = "gemm: split epilogue needs bf16 output, addend_hi, and out_lo / addend_lo both set or both null";
+      return cudaErrorInvalidValue;
+    }
+    if ((reinterpret_cast<uintptr_t>(c.addend_hi) & 15) || (reinterpret_cast<uintptr_t>(c.addend_lo) & 15) ||
+        (reinterpret_cast<uintptr_t>(c.out_lo) & 15)) {
+      *why = "gemm: split operands must be 16-byte aligned";
+      return cudaErrorInvalidValue;
+    }
+  } else if (c.out_lo || c.addend_hi || c.addend_lo) {
+    *why = "gemm: out_lo / addend_hi / addend_lo need split = 1";
+    return cudaErrorInvalidValue;
+  }
   // Tile shape: 256-wide tiles on CTA pairs when there is enough work to fill the machine (batch throughput);
   // for latency-bound small problems (streaming: one or a few chunks) fall back to shapes that make more tiles.
   if (c.cta_group != 0 && c.cta_group != 1 && c.cta_group != 2) { *why = "gemm: cta_group must be 0, 1 or 2"; return cudaErrorInvalidValue; }
@@ -558,23 +707,24 @@ cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, con
   p.add_bcast = c.addend_bcast;
   p.rows = c.rows;
   p.n = c.n;
+  p.has_lo = (c.split && c.out_lo) ? 1 : 0;
   if (c.ln_stats_out) {
-    if (!c.out_f32 || !c.ln_xb || (reinterpret_cast<uintptr_t>(c.ln_xb) & 15) || (reinterpret_cast<uintptr_t>(c.ln_stats_out) & 7)) {
-      *why = "gemm: LayerNorm emit needs fp32 output and 16-byte aligned ln_xb";
+    if (!c.split || (reinterpret_cast<uintptr_t>(c.ln_stats_out) & 7)) {
+      *why = "gemm: LayerNorm statistics are emitted by the split epilogue only (8-byte aligned buffer)";
       return cudaErrorInvalidValue;
     }
-    p.ln_xb = static_cast<__nv_bfloat16*>(c.ln_xb);
     p.ln_stats_out = static_cast<float2*>(c.ln_stats_out);
-    if (c.ln_parts_out) *c.ln_parts_out = 2 * p.tiles_n;
+    if (c.ln_parts_out) *c.ln_parts_out = c.n / 64;
   }
   if (c.ln_stats_in) {
-    if (c.out_f32 || !c.ln_c1 || c.ln_parts_in <= 0 || c.mode != kGemmPlain) {
-      *why = "gemm: LayerNorm-folded input needs bf16 output, ln_c1 and ln_parts_in";
+    if (c.out_f32 || c.split || !c.ln_c1 || c.ln_parts_in <= 0 || c.mode != kGemmPlain || c.a_inner % c.ln_parts_in != 0) {
+      *why = "gemm: LayerNorm-folded input needs bf16 output, ln_c1 and ln_parts_in dividing K";
       return cudaErrorInvalidValue;
     }
     p.ln_stats_in = static_cast<const float2*>(c.ln_stats_in);
     p.ln_c1 = c.ln_c1;
     p.ln_parts_in = c.ln_parts_in;
+    p.ln_part_n = static_cast<float>(c.a_inner / c.ln_parts_in);
     p.ln_inv_k = 1.0f / static_cast<float>(c.a_inner);
     p.ln_eps = c.ln_eps;
   }
@@ -617,6 +767,18 @@ cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, con
     uint32_t box[3] = {32u, static_cast<uint32_t>(kBM), 1};
     r = encode_tmap(&p.tm_add, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, c.addend, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
     if (r != CUDA_SUCCESS) { *why = "gemm: cuTensorMapEncodeTiled(addend) failed"; return cudaErrorInvalidValue; }
+  }
+  if (c.split) {
+    uint32_t box[3] = {64u, static_cast<uint32_t>(kBM), 1};
+    uint64_t odims[3] = {static_cast<uint64_t>(c.n), static_cast<uint64_t>(c.rows), static_cast<uint64_t>(c.nbatch)};
+    uint64_t ostr[2] = {odims[0] * 2, odims[0] * odims[1] * 2};
+    uint64_t adims[3] = {odims[0], odims[1], static_cast<uint64_t>(c.addend_bcast ? 1 : c.nbatch)};
+    r = encode_tmap(&p.tm_add, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.addend_hi, adims, ostr, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r == CUDA_SUCCESS && c.addend_lo)
+      r = encode_tmap(&p.tm_add2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.addend_lo, adims, ostr, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r == CUDA_SUCCESS && c.out_lo)
+      r = encode_tmap(&p.tm_out2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.out_lo, odims, ostr, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (r != CUDA_SUCCESS) { *why = "gemm: cuTensorMapEncodeTiled(split operands) failed"; return cudaErrorInvalidValue; }
   }
 
   if (bn == 256) return cg == 2 ? dispatch_epilogue<256, 2>(c, p, num_sms, stream) : dispatch_epilogue<256, 1>(c, p, num_sms, stream);

@@ -33,13 +33,21 @@ struct GemmCall {
   void* out = nullptr;              // [nbatch*rows, n]
   int out_f32 = 0;
   int cta_group = 0;                // 0 = default, 1, 2
-  // ---- optional LayerNorm fusion.  A residual GEMM (fp32 out) can EMIT what the LayerNorm of its output needs: a
-  // bf16 copy of the rows (ln_xb, [nbatch*rows, n]) and, per row, 2 * (n / tile width) partial (sum, sum of squares)
-  // pairs (ln_stats_out; *ln_parts_out receives the count).  The GEMM that consumes LN(x) W^T then runs on the bf16
-  // copy with gamma folded into W and applies  out = rstd * (acc - mean * c1[n]) + bias[n]  in its epilogue (bf16 out),
-  // c1[n] = sum_k W'[n][k], bias[n] = b[n] + sum_k beta[k] W[n][k]; mean / rstd come from the partials (ln_stats_in,
-  // ln_parts_in per row, summed in a fixed order).
-  void* ln_xb = nullptr;
+  // ---- split residual stream + LayerNorm fusion (the default encoder path).
+  // The residual stream x is kept as TWO bf16 arrays, x = hi + lo (hi = bf16(x), lo = bf16(x - hi): 16 mantissa bits
+  // at the HBM cost of one fp32 array).  A residual GEMM with `split` set computes
+  //     x' = act(acc + bias) + (addend_hi + addend_lo)      (fp32 in registers)
+  // and writes out = hi(x'), out_lo = lo(x') (out_lo / addend_lo may be null: plain bf16 stream).  `hi` IS the bf16 A
+  // operand of the GEMM that consumes LN(x'), so no LayerNorm kernel and no extra copy exist: the residual GEMM also
+  // emits, per row, n / 64 partial statistics (mean_i, M2_i) of its hi values, one per 64 columns (independent of the tile shape)
+  // (ln_stats_out; *ln_parts_out receives the count), and the consuming GEMM runs on hi with gamma folded into W and
+  // applies  out = rstd * (acc - mean * c1[n]) + bias[n]  in its epilogue (bf16 out), c1[n] = sum_k W'[n][k],
+  // bias[n] = b[n] + sum_k beta[k] W[n][k]; mean / rstd are combined from the partials (ln_stats_in, ln_parts_in per
+  // row) with Chan's parallel-variance formula in a fixed order.
+  int split = 0;
+  void* out_lo = nullptr;
+  const void* addend_hi = nullptr;  // bf16 [nbatch*rows, n] (or [rows, n] with addend_bcast)
+  const void* addend_lo = nullptr;
   void* ln_stats_out = nullptr;
   int* ln_parts_out = nullptr;
   const void* ln_stats_in = nullptr;

@@ -11,21 +11,36 @@ namespace {
 
 constexpr int kMaxVec = 10;  // d <= 1280
 
-template <bool OUT_F32>
-__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g,
-                                                        const float* __restrict__ bta, void* __restrict__ y,
-                                                        long long rows, int d) {
+__device__ __forceinline__ float4 bf16x4_to_f32(uint2 w) {
+  return make_float4(__uint_as_float(w.x << 16), __uint_as_float(w.x & 0xffff0000u), __uint_as_float(w.y << 16),
+                     __uint_as_float(w.y & 0xffff0000u));
+}
+
+// SPLIT_IN: the row is the split residual stream x = hi + lo (two bf16 arrays, `x` = hi, `x_lo` = lo or null)
+template <bool OUT_F32, bool SPLIT_IN>
+__global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__ x, const void* __restrict__ x_lo,
+                                                        const float* __restrict__ g, const float* __restrict__ bta,
+                                                        void* __restrict__ y, long long rows, int d) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nvec = d >> 7;  // float4 per lane
-  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
   float4 v[kMaxVec];
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     if (i < nvec) {
-      v[i] = __ldg(xr + i * 32 + lane);
+      if constexpr (SPLIT_IN) {
+        const uint2* hr = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(x) + row * d);
+        v[i] = bf16x4_to_f32(__ldg(hr + i * 32 + lane));
+        if (x_lo) {
+          const uint2* lr = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(x_lo) + row * d);
+          const float4 l = bf16x4_to_f32(__ldg(lr + i * 32 + lane));
+          v[i].x += l.x; v[i].y += l.y; v[i].z += l.z; v[i].w += l.w;
+        }
+      } else {
+        v[i] = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(x) + row * d) + i * 32 + lane);
+      }
       sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
@@ -74,9 +89,21 @@ cudaError_t layernorm_launch(const float* x, const float* g, const float* b, voi
   if (rows <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
   if (out_f32)
-    layernorm_kernel<true><<<grid, 256, 0, stream>>>(x, g, b, y, rows, d);
+    layernorm_kernel<true, false><<<grid, 256, 0, stream>>>(x, nullptr, g, b, y, rows, d);
   else
-    layernorm_kernel<false><<<grid, 256, 0, stream>>>(x, g, b, y, rows, d);
+    layernorm_kernel<false, false><<<grid, 256, 0, stream>>>(x, nullptr, g, b, y, rows, d);
+  return cudaGetLastError();
+}
+
+cudaError_t layernorm_split_launch(const void* x_hi, const void* x_lo, const float* g, const float* b, void* y,
+                                   long long rows, int d, int out_f32, cudaStream_t stream) {
+  if (d % 128 != 0 || d <= 0 || d > 128 * kMaxVec) return cudaErrorInvalidValue;
+  if (rows <= 0) return cudaSuccess;
+  const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
+  if (out_f32)
+    layernorm_kernel<true, true><<<grid, 256, 0, stream>>>(x_hi, x_lo, g, b, y, rows, d);
+  else
+    layernorm_kernel<false, true><<<grid, 256, 0, stream>>>(x_hi, x_lo, g, b, y, rows, d);
   return cudaGetLastError();
 }
 

@@ -362,8 +362,8 @@ __device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
   return r;
 }
-// gelu_erf on two values at once (same arithmetic as gelu_erf, FMA-pipe work issued as packed pairs); returns bf16x2
-__device__ __forceinline__ uint32_t gelu_erf_bf16x2(f32x2_t x) {
+// gelu_erf on two values at once (same arithmetic as gelu_erf, FMA-pipe work issued as packed pairs)
+__device__ __forceinline__ f32x2_t gelu_erf_f32x2(f32x2_t x) {
   float x0, x1;
   unpack2(x, x0, x1);
   const f32x2_t nax = pack2(-fabsf(x0), -fabsf(x1));
@@ -377,8 +377,12 @@ __device__ __forceinline__ uint32_t gelu_erf_bf16x2(f32x2_t x) {
   p = fma2(p, t, pack2(-0.142248368f, -0.142248368f));
   p = fma2(p, t, pack2(0.127414796f, 0.127414796f));
   const f32x2_t h = mul2(mul2(p, t), e);
+  return fma2(nax, h, pack2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
+}
+// ... returning bf16x2
+__device__ __forceinline__ uint32_t gelu_erf_bf16x2(f32x2_t x) {
   float r0, r1;
-  unpack2(fma2(nax, h, pack2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f))), r0, r1);
+  unpack2(gelu_erf_f32x2(x), r0, r1);
   return pack_bf16x2(r0, r1);
 }
 

@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "attention_sm100.h"
 #include "fft400.cuh"
 #include "frontend_logmel.h"
@@ -83,6 +85,15 @@ __global__ void fold_ln_kernel(__nv_bfloat16* dst, const __nv_bfloat16* src, int
     c1[n] = s1;
     c2[n] = s2 + (bias ? bias[n] * scale : 0.f);
   }
+}
+// fp32 -> split pair: hi = bf16(x), lo = bf16(x - hi)
+__global__ void split_f32_kernel(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* src, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = src[i];
+  const __nv_bfloat16 h = __float2bfloat16(v);
+  hi[i] = h;
+  if (lo) lo[i] = __float2bfloat16(v - __bfloat162float(h));
 }
 // conv weight [n_out, c_in, 3] -> tap-major [n_out, 3 * c_pad] (zero padded channels)
 __global__ void pack_conv_kernel(__nv_bfloat16* dst, const __nv_bfloat16* src, int n_out, int c_in, int c_pad) {
@@ -242,7 +253,7 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
   char* pdev = static_cast<char*>(h->table_mem);
   auto put = [&](const void* src, size_t n) -> const void* {
     void* dst = pdev;
-    cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dst, src, n, cudaMemcpyHostToDevice);
     pdev += n;
     return dst;
   };
@@ -252,7 +263,7 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
   h->tables.mel_op_off = static_cast<const int*>(put(op_off.data(), sizeof(int) * (kMelWarps + 1)));
   h->tables.mel_m0 = static_cast<const int*>(put(warp_m0.data(), sizeof(int) * (kMelWarps + 1)));
   h->max_batch = 1 << 14;
-  e = cudaMalloc(&h->chunk_max, sizeof(unsigned) * h->max_batch);
+  if (e == cudaSuccess) e = cudaMalloc(&h->chunk_max, sizeof(unsigned) * h->max_batch);
   if (e == cudaSuccess) e = cudaMalloc(&h->tile_min, sizeof(float) * h->max_batch * frontend_tiles(n_samples));
   if (e == cudaSuccess) e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
@@ -387,10 +398,16 @@ struct LayerDev {
   const float *c1_qkv = nullptr, *c1_fc1 = nullptr;   // column sums of the folded weights
 };
 
-#ifndef TTASR_FUSE_LN_DEFAULT
-#define TTASR_FUSE_LN_DEFAULT 0
+// How the residual stream x is held between the blocks (ttasr_encoder_create_ex / TTASR_RESIDUAL):
+//   split (default): two bf16 arrays hi + lo; the per-layer LayerNorms are folded into the QKV / fc1 GEMMs, whose A
+//                    operand is `hi` itself; statistics come from the residual GEMMs' epilogues.  No LayerNorm kernel
+//                    between the blocks, residual traffic = one fp32 array.
+//   f32:             fp32 array + a LayerNorm kernel before each QKV / fc1 GEMM (the reference-precision path)
+//   bf16:            `hi` only (what an all-bf16 Hugging Face run does); half the residual traffic, measured in
+//                    DESIGN.md, not the default
+#ifndef TTASR_RESIDUAL_DEFAULT
+#define TTASR_RESIDUAL_DEFAULT TTASR_RESIDUAL_SPLIT
 #endif
-constexpr bool kFuseLnDefault = TTASR_FUSE_LN_DEFAULT != 0;
 
 enum ProfileKind { kProfPrep = 0, kProfConv1, kProfConv2, kProfLayerNorm, kProfQkv, kProfAttention, kProfOutProj,
                    kProfFc1, kProfFc2, kProfKinds };
@@ -418,9 +435,10 @@ struct ttasr_encoder {
   int device = 0, num_sms = 0;
   ttasr_encoder_cfg cfg{};
   int c1_pad = 128;        // conv1 input channels padded per tap
-  bool fuse_ln = false;    // per-layer LayerNorms folded into the QKV / fc1 GEMMs (TTASR_FUSE_LN, see encoder_create)
+  int residual = TTASR_RESIDUAL_SPLIT;
+  bool fuse_ln = true;     // residual != f32: per-layer LayerNorms folded into the QKV / fc1 GEMMs
   void* arena = nullptr;   // all packed weights
-  const __nv_bfloat16 *conv1_w = nullptr, *conv2_w = nullptr;
+  const __nv_bfloat16 *conv1_w = nullptr, *conv2_w = nullptr, *pos_hi = nullptr, *pos_lo = nullptr;
   const float *conv1_b = nullptr, *conv2_b = nullptr, *pos = nullptr, *lnp_g = nullptr, *lnp_b = nullptr;
   std::vector<LayerDev> layers;
 };
@@ -428,23 +446,23 @@ struct ttasr_encoder {
 namespace {
 
 struct WsLayout {
-  size_t x, h, qkv, ffn, xb, st0, st1, total;
+  size_t x, h, qkv, ffn, st0, st1, total;
 };
 WsLayout ws_layout(const ttasr_encoder_cfg& c, int64_t B, bool fuse_ln) {
   auto up = [](size_t v) { return (v + 1023) & ~static_cast<size_t>(1023); };
   const size_t rows = static_cast<size_t>(B) * c.n_ctx;
   WsLayout w;
   size_t o = 0;
-  w.x = o;   o += up(rows * c.d_model * 4);
+  // residual stream: fp32 [rows, d], or the split pair hi | lo (two bf16 [rows, d] halves of the same region)
+  w.x = o;   o += up(rows * c.d_model * 2) * 2;
   w.h = o;   o += up(rows * c.d_model * 2);
   // qkv region also hosts the bf16 time-major features of the stem (2*n_ctx x 128 <= n_ctx x 3d)
   w.qkv = o; o += up(std::max(rows * 3 * c.d_model * 2, rows * 2 * 128 * 2));
   // ffn region also hosts conv1's output [B, 2*n_ctx, d] (ffn >= 2d always holds for Whisper; guarded in create)
   w.ffn = o; o += up(std::max(rows * c.ffn_dim * 2, rows * 2 * c.d_model * 2));
-  w.xb = w.st0 = w.st1 = o;
-  if (fuse_ln) {  // bf16 copy of the residual stream + two sets of per-row LayerNorm partials (<= 2 * d/128 per row)
-    const size_t parts = 2 * static_cast<size_t>(c.d_model / 128);
-    w.xb = o;  o += up(rows * c.d_model * 2);
+  w.st0 = w.st1 = o;
+  if (fuse_ln) {  // two sets of per-row LayerNorm partials (d/64 (mean, M2) pairs per row)
+    const size_t parts = static_cast<size_t>(c.d_model / 64);
     w.st0 = o; o += up(rows * parts * 8);
     w.st1 = o; o += up(rows * parts * 8);
   }
@@ -457,8 +475,25 @@ WsLayout ws_layout(const ttasr_encoder_cfg& c, int64_t B, bool fuse_ln) {
 extern "C" {
 
 int ttasr_encoder_create(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, ttasr_encoder_t** out) {
+  return ttasr_encoder_create_ex(cfg, w, TTASR_RESIDUAL_AUTO, out);
+}
+
+int ttasr_encoder_create_ex(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, int residual, ttasr_encoder_t** out) {
   if (!cfg || !w || !out || !w->layers) return fail(TTASR_E_ARG, "encoder_create: null argument");
   *out = nullptr;
+  if (residual == TTASR_RESIDUAL_AUTO) {
+    residual = TTASR_RESIDUAL_DEFAULT;
+    if (const char* env = getenv("TTASR_RESIDUAL")) {
+      if (!strcmp(env, "f32")) residual = TTASR_RESIDUAL_F32;
+      else if (!strcmp(env, "split")) residual = TTASR_RESIDUAL_SPLIT;
+      else if (!strcmp(env, "bf16")) residual = TTASR_RESIDUAL_BF16;
+      else return fail(TTASR_E_ARG, "encoder_create: TTASR_RESIDUAL must be f32, split or bf16 (got '%s')", env);
+    } else if (const char* env2 = getenv("TTASR_FUSE_LN")) {   // round-1 switch, kept: 0 selects the fp32 stream
+      residual = atoi(env2) != 0 ? TTASR_RESIDUAL_SPLIT : TTASR_RESIDUAL_F32;
+    }
+  }
+  if (residual != TTASR_RESIDUAL_F32 && residual != TTASR_RESIDUAL_SPLIT && residual != TTASR_RESIDUAL_BF16)
+    return fail(TTASR_E_ARG, "encoder_create: bad residual mode %d", residual);
   const int d = cfg->d_model, f = cfg->ffn_dim, L = cfg->n_layers;
   if (d <= 0 || d % 128 != 0 || d > 1280) return fail(TTASR_E_SHAPE, "encoder_create: d_model must be a multiple of 128, <= 1280 (got %d)", d);
   if (cfg->n_heads <= 0 || d != cfg->n_heads * 64) return fail(TTASR_E_SHAPE, "encoder_create: head_dim must be 64 (d_model %d, heads %d)", d, cfg->n_heads);
@@ -482,15 +517,14 @@ int ttasr_encoder_create(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, t
   h->device = device;
   h->num_sms = sms;
   h->cfg = *cfg;
-  {
-    const char* env = getenv("TTASR_FUSE_LN");
-    h->fuse_ln = env ? (atoi(env) != 0) : kFuseLnDefault;
-  }
+  h->residual = residual;
+  h->fuse_ln = residual != TTASR_RESIDUAL_F32;
   const size_t dd = static_cast<size_t>(d) * d;
   size_t bytes = 0;
   auto up = [](size_t v) { return (v + 255) & ~static_cast<size_t>(255); };
   const size_t conv1_bytes = up(static_cast<size_t>(d) * 3 * h->c1_pad * 2), conv2_bytes = up(3 * dd * 2);
-  bytes += conv1_bytes + conv2_bytes + 2 * up(d * 4) + up(static_cast<size_t>(cfg->n_ctx) * d * 4) + 2 * up(d * 4);
+  bytes += conv1_bytes + conv2_bytes + 2 * up(d * 4) + up(static_cast<size_t>(cfg->n_ctx) * d * 4) + 2 * up(d * 4) +
+           2 * up(static_cast<size_t>(cfg->n_ctx) * d * 2);
   const size_t per_layer = up(3 * dd * 2) + up(dd * 2) + 2 * up(static_cast<size_t>(d) * f * 2) + 4 * up(d * 4) +
                            up(3 * d * 4) + up(d * 4) + up(f * 4) + up(d * 4) + up(3 * d * 4) + up(f * 4);
   bytes += per_layer * L;
@@ -520,6 +554,14 @@ int ttasr_encoder_create(const ttasr_encoder_cfg* cfg, const ttasr_weights* w, t
   h->conv1_b = copy_f32(w->conv1_b, d, 1.f);
   h->conv2_b = copy_f32(w->conv2_b, d, 1.f);
   h->pos = copy_f32(w->pos, static_cast<size_t>(cfg->n_ctx) * d, 1.f);
+  if (h->fuse_ln) {  // the positional table as a split pair: it is the "residual" the conv stem's epilogue adds
+    const size_t n = static_cast<size_t>(cfg->n_ctx) * d;
+    __nv_bfloat16* ph = reinterpret_cast<__nv_bfloat16*>(take(n * 2));
+    __nv_bfloat16* pl = residual == TTASR_RESIDUAL_SPLIT ? reinterpret_cast<__nv_bfloat16*>(take(n * 2)) : nullptr;
+    split_f32_kernel<<<blocks_for(static_cast<long long>(n), 256), 256>>>(ph, pl, w->pos, static_cast<long long>(n));
+    h->pos_hi = ph;
+    h->pos_lo = pl;
+  }
   h->lnp_g = copy_f32(w->ln_post_g, d, 1.f);
   h->lnp_b = copy_f32(w->ln_post_b, d, 1.f);
   h->layers.resize(L);
@@ -611,7 +653,9 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(wsb + ws.qkv);
   __nv_bfloat16* ffn = reinterpret_cast<__nv_bfloat16*>(wsb + ws.ffn);
   const bool fuse = h->fuse_ln;
-  __nv_bfloat16* xb = reinterpret_cast<__nv_bfloat16*>(wsb + ws.xb);   // bf16 copy of x (LayerNorm-fused mode)
+  const size_t half = (static_cast<size_t>(batch) * c.n_ctx * c.d_model * 2 + 1023) & ~static_cast<size_t>(1023);
+  __nv_bfloat16* xh = reinterpret_cast<__nv_bfloat16*>(wsb + ws.x);            // split residual stream: hi ...
+  __nv_bfloat16* xl = h->residual == TTASR_RESIDUAL_SPLIT ? reinterpret_cast<__nv_bfloat16*>(wsb + ws.x + half) : nullptr;  // ... lo
   void* st0 = wsb + ws.st0;   // LayerNorm partials of x as the attention block sees it (LN1)
   void* st1 = wsb + ws.st1;   // ... as the MLP block sees it (LN2)
   int parts0 = 0, parts1 = 0;
@@ -622,6 +666,7 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
   ProfileState& prof = h->prof;
   ProfileState::Span span{};
   auto prof_begin = [&](int kind) {
+    nvtxRangePushA(kProfNames[kind]);
     if (!prof.on) return;
     span.kind = kind;
     span.a = prof.get();
@@ -629,6 +674,7 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
     cudaEventRecord(span.a, stream);
   };
   auto prof_end = [&]() {
+    nvtxRangePop();
     if (!prof.on) return;
     cudaEventRecord(span.b, stream);
     prof.pending.push_back(span);
@@ -637,8 +683,8 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
   do {                                                                                                            \
     prof_begin(kind);                                                                                             \
     e = gemm_launch(call, h->num_sms, stream, &why);                                                              \
-    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: %s: %s", name, why ? why : cudaGetErrorString(e)); \
     prof_end();                                                                                                   \
+    if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: %s: %s", name, why ? why : cudaGetErrorString(e)); \
   } while (0)
 
   // ---- stem input as bf16 time-major
@@ -673,11 +719,25 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
     g.mode = kGemmConv2;
     g.a = c1; g.lda = d; g.a_inner = d; g.rows = T; g.nbatch = B;
     g.w = h->conv2_w; g.n = d; g.kb_per_tap = d / 64; g.k_blocks = 3 * g.kb_per_tap;
-    g.bias = h->conv2_b; g.act = 1; g.addend = h->pos; g.addend_bcast = 1; g.out = x; g.out_f32 = 1;
-    if (fuse) { g.ln_xb = xb; g.ln_stats_out = st0; g.ln_parts_out = &parts0; }
+    g.bias = h->conv2_b; g.act = 1; g.addend_bcast = 1;
+    if (fuse) {
+      g.split = 1; g.addend_hi = h->pos_hi; g.addend_lo = h->pos_lo; g.out = xh; g.out_lo = xl;
+      g.ln_stats_out = st0; g.ln_parts_out = &parts0;
+    } else {
+      g.addend = h->pos; g.out = x; g.out_f32 = 1;
+    }
     GEMM_TRY(g, "conv2", kProfConv2);
   }
   const long long M = static_cast<long long>(B) * T;
+  // residual GEMM: x += a W^T + b, on whichever representation of x this handle uses
+  auto residual_gemm = [&](GemmCall& g, void* stats, int* parts) {
+    if (fuse) {
+      g.split = 1; g.addend_hi = xh; g.addend_lo = xl; g.out = xh; g.out_lo = xl;
+      g.ln_stats_out = stats; g.ln_parts_out = parts;
+    } else {
+      g.addend = x; g.out = x; g.out_f32 = 1;
+    }
+  };
   for (int i = 0; i < c.n_layers; ++i) {
     const LayerDev& l = h->layers[i];
     if (!fuse) {
@@ -688,7 +748,7 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
     }
     {
       GemmCall g;
-      g.a = fuse ? xb : hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
+      g.a = fuse ? xh : hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.wqkv; g.n = 3 * d; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.bqkv; g.out = qkv;
       if (fuse) { g.ln_stats_in = st0; g.ln_parts_in = parts0; g.ln_c1 = l.c1_qkv; }
@@ -702,8 +762,8 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
       GemmCall g;
       g.a = hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.wo; g.n = d; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
-      g.bias = l.bo; g.addend = x; g.out = x; g.out_f32 = 1;
-      if (fuse) { g.ln_xb = xb; g.ln_stats_out = st1; g.ln_parts_out = &parts1; }
+      g.bias = l.bo;
+      residual_gemm(g, st1, &parts1);
       GEMM_TRY(g, "out_proj", kProfOutProj);
     }
     if (!fuse) {
@@ -714,7 +774,7 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
     }
     {
       GemmCall g;
-      g.a = fuse ? xb : hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
+      g.a = fuse ? xh : hbuf; g.lda = d; g.a_inner = d; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.w1; g.n = f; g.k_blocks = d / 64; g.kb_per_tap = g.k_blocks;
       g.bias = l.b1; g.act = 1; g.out = ffn;
       if (fuse) { g.ln_stats_in = st1; g.ln_parts_in = parts1; g.ln_c1 = l.c1_fc1; }
@@ -724,13 +784,14 @@ int ttasr_encoder_forward(const ttasr_encoder_t* h, const void* feats_dev, int f
       GemmCall g;
       g.a = ffn; g.lda = f; g.a_inner = f; g.rows = static_cast<int>(M); g.nbatch = 1;
       g.w = l.w2; g.n = d; g.k_blocks = f / 64; g.kb_per_tap = g.k_blocks;
-      g.bias = l.b2; g.addend = x; g.out = x; g.out_f32 = 1;
-      if (fuse && i + 1 < c.n_layers) { g.ln_xb = xb; g.ln_stats_out = st0; g.ln_parts_out = &parts0; }
+      g.bias = l.b2;
+      residual_gemm(g, (i + 1 < c.n_layers) ? st0 : nullptr, &parts0);  // the last block feeds the final LayerNorm kernel
       GEMM_TRY(g, "fc2", kProfFc2);
     }
   }
   prof_begin(kProfLayerNorm);
-  e = layernorm_launch(x, h->lnp_g, h->lnp_b, out_dev, M, d, out_dtype == TTASR_OUT_F32, stream);
+  e = fuse ? layernorm_split_launch(xh, xl, h->lnp_g, h->lnp_b, out_dev, M, d, out_dtype == TTASR_OUT_F32, stream)
+           : layernorm_launch(x, h->lnp_g, h->lnp_b, out_dev, M, d, out_dtype == TTASR_OUT_F32, stream);
   prof_end();
   if (e != cudaSuccess) return fail(TTASR_E_CUDA, "encoder_forward: final layer norm: %s", cudaGetErrorString(e));
 #undef GEMM_TRY
@@ -787,15 +848,11 @@ int ttasr_op_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, c
   CUDA_TRY(cudaGetDevice(&device));
   int rc = check_arch(device, &sms);
   if (rc != TTASR_OK) return rc;
-  static thread_local float* zero_bias = nullptr;
-  static thread_local int64_t zero_n = 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* zero_bias = nullptr;  // stream-ordered scratch, freed right behind the launch
   if (!bias_dev) {
-    if (zero_n < N) {
-      if (zero_bias) cudaFree(zero_bias);
-      CUDA_TRY(cudaMalloc(&zero_bias, sizeof(float) * N));
-      CUDA_TRY(cudaMemset(zero_bias, 0, sizeof(float) * N));
-      zero_n = N;
-    }
+    CUDA_TRY(cudaMallocAsync(&zero_bias, sizeof(float) * N, st));
+    CUDA_TRY(cudaMemsetAsync(zero_bias, 0, sizeof(float) * N, st));
     bias_dev = zero_bias;
   }
   GemmCall g;
@@ -804,8 +861,94 @@ int ttasr_op_gemm(const void* a_dev, const void* w_dev, const float* bias_dev, c
   g.bias = bias_dev; g.addend = addend_dev; g.act = act; g.out = out_dev; g.out_f32 = (out_dtype == TTASR_OUT_F32);
   g.cta_group = cta_group;
   const char* why = nullptr;
-  cudaError_t e = gemm_launch(g, sms, static_cast<cudaStream_t>(stream), &why);
+  cudaError_t e = gemm_launch(g, sms, st, &why);
+  if (zero_bias) cudaFreeAsync(zero_bias, st);
   if (e != cudaSuccess) return fail(why ? TTASR_E_ARG : TTASR_E_CUDA, "op_gemm: %s", why ? why : cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+int ttasr_op_gemm_split(const void* a_dev, const void* w_dev, const float* bias_dev, const void* addh_dev,
+                        const void* addl_dev, void* outh_dev, void* outl_dev, void* stats_out_dev, int64_t M, int64_t N,
+                        int64_t K, int act, int cta_group, void* stream) {
+  if (!a_dev || !w_dev || !bias_dev || !addh_dev || !outh_dev) return fail(TTASR_E_ARG, "op_gemm_split: null buffer");
+  if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0 || N % 128 != 0 || M > 0x7fffffff)
+    return fail(TTASR_E_SHAPE, "op_gemm_split: need M > 0, N %% 128 == 0, K %% 64 == 0 (got %lld, %lld, %lld)", (long long)M, (long long)N, (long long)K);
+  int device = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  int rc = check_arch(device, &sms);
+  if (rc != TTASR_OK) return rc;
+  GemmCall g;
+  g.a = a_dev; g.lda = K; g.a_inner = static_cast<int>(K); g.rows = static_cast<int>(M); g.nbatch = 1;
+  g.w = w_dev; g.n = static_cast<int>(N); g.k_blocks = static_cast<int>(K / 64); g.kb_per_tap = g.k_blocks;
+  g.bias = bias_dev; g.act = act; g.split = 1; g.addend_hi = addh_dev; g.addend_lo = addl_dev;
+  g.out = outh_dev; g.out_lo = outl_dev; g.ln_stats_out = stats_out_dev; g.cta_group = cta_group;
+  const char* why = nullptr;
+  cudaError_t e = gemm_launch(g, sms, static_cast<cudaStream_t>(stream), &why);
+  if (e != cudaSuccess) return fail(why ? TTASR_E_ARG : TTASR_E_CUDA, "op_gemm_split: %s", why ? why : cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+int ttasr_op_gemm_lnfold(const void* a_dev, const void* w_dev, const float* c1_dev, const float* c2_dev,
+                         const void* stats_in_dev, int parts, void* out_dev, int64_t M, int64_t N, int64_t K, int act,
+                         float eps, int cta_group, void* stream) {
+  if (!a_dev || !w_dev || !c1_dev || !c2_dev || !stats_in_dev || !out_dev) return fail(TTASR_E_ARG, "op_gemm_lnfold: null buffer");
+  if (M <= 0 || N <= 0 || K <= 0 || K % 64 != 0 || N % 128 != 0 || M > 0x7fffffff || parts <= 0 || K % parts != 0)
+    return fail(TTASR_E_SHAPE, "op_gemm_lnfold: need M > 0, N %% 128 == 0, K %% 64 == 0, parts | K (got %lld, %lld, %lld, %d)", (long long)M, (long long)N, (long long)K, parts);
+  int device = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  int rc = check_arch(device, &sms);
+  if (rc != TTASR_OK) return rc;
+  GemmCall g;
+  g.a = a_dev; g.lda = K; g.a_inner = static_cast<int>(K); g.rows = static_cast<int>(M); g.nbatch = 1;
+  g.w = w_dev; g.n = static_cast<int>(N); g.k_blocks = static_cast<int>(K / 64); g.kb_per_tap = g.k_blocks;
+  g.bias = c2_dev; g.act = act; g.out = out_dev; g.ln_stats_in = stats_in_dev; g.ln_parts_in = parts; g.ln_c1 = c1_dev;
+  g.ln_eps = eps; g.cta_group = cta_group;
+  const char* why = nullptr;
+  cudaError_t e = gemm_launch(g, sms, static_cast<cudaStream_t>(stream), &why);
+  if (e != cudaSuccess) return fail(why ? TTASR_E_ARG : TTASR_E_CUDA, "op_gemm_lnfold: %s", why ? why : cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+int ttasr_op_conv_stem(const void* feats_tm_dev, int ld, int n_mels, int64_t B, int T, int d, const void* conv1_w_dev,
+                       const float* conv1_b_dev, const void* conv2_w_dev, const float* conv2_b_dev, const float* pos_dev,
+                       void* scratch_dev, float* out_dev, void* stream) {
+  if (!feats_tm_dev || !conv1_w_dev || !conv1_b_dev || !conv2_w_dev || !conv2_b_dev || !pos_dev || !scratch_dev || !out_dev)
+    return fail(TTASR_E_ARG, "op_conv_stem: null buffer");
+  if (B <= 0 || T <= 0 || d <= 0 || d % 128 != 0 || n_mels <= 0 || n_mels > 128 || ld < n_mels || ld % 8 != 0)
+    return fail(TTASR_E_SHAPE, "op_conv_stem: need d %% 128 == 0, n_mels <= 128 <= ld-compatible, ld %% 8 == 0");
+  int device = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&device));
+  int rc = check_arch(device, &sms);
+  if (rc != TTASR_OK) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int c1_pad = 128;
+  __nv_bfloat16 *w1 = nullptr, *w2 = nullptr;
+  CUDA_TRY(cudaMallocAsync(&w1, static_cast<size_t>(d) * 3 * c1_pad * 2, st));
+  cudaError_t e = cudaMallocAsync(&w2, static_cast<size_t>(d) * 3 * d * 2, st);
+  if (e != cudaSuccess) { cudaFreeAsync(w1, st); return fail(TTASR_E_NOMEM, "op_conv_stem: %s", cudaGetErrorString(e)); }
+  pack_conv_kernel<<<blocks_for(static_cast<long long>(d) * 3 * c1_pad, 256), 256, 0, st>>>(
+      w1, static_cast<const __nv_bfloat16*>(conv1_w_dev), d, n_mels, c1_pad);
+  pack_conv_kernel<<<blocks_for(3LL * d * d, 256), 256, 0, st>>>(w2, static_cast<const __nv_bfloat16*>(conv2_w_dev), d, d, d);
+  const char* why = nullptr;
+  {
+    GemmCall g;
+    g.mode = kGemmConv1;
+    g.a = feats_tm_dev; g.lda = ld; g.a_inner = n_mels; g.rows = 2 * T; g.nbatch = static_cast<int>(B);
+    g.w = w1; g.n = d; g.kb_per_tap = c1_pad / 64; g.k_blocks = 3 * g.kb_per_tap;
+    g.bias = conv1_b_dev; g.act = 1; g.out = scratch_dev; g.out_f32 = 0;
+    e = gemm_launch(g, sms, st, &why);
+  }
+  if (e == cudaSuccess) {
+    GemmCall g;
+    g.mode = kGemmConv2;
+    g.a = scratch_dev; g.lda = d; g.a_inner = d; g.rows = T; g.nbatch = static_cast<int>(B);
+    g.w = w2; g.n = d; g.kb_per_tap = d / 64; g.k_blocks = 3 * g.kb_per_tap;
+    g.bias = conv2_b_dev; g.act = 1; g.addend = pos_dev; g.addend_bcast = 1; g.out = out_dev; g.out_f32 = 1;
+    e = gemm_launch(g, sms, st, &why);
+  }
+  cudaFreeAsync(w1, st);
+  cudaFreeAsync(w2, st);
+  if (e != cudaSuccess) return fail(why ? TTASR_E_ARG : TTASR_E_CUDA, "op_conv_stem: %s", why ? why : cudaGetErrorString(e));
   return TTASR_OK;
 }
 

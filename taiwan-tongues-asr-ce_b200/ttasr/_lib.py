@@ -13,6 +13,9 @@ TTASR_OK = 0
 PCM_F32, PCM_I16 = 0, 1
 FEATS_F32_MEL_MAJOR, FEATS_BF16_TIME_MAJOR = 0, 1
 OUT_BF16, OUT_F32 = 0, 1
+RESIDUAL_AUTO, RESIDUAL_F32, RESIDUAL_SPLIT, RESIDUAL_BF16 = -1, 0, 1, 2
+RESIDUAL_MODES = {None: RESIDUAL_AUTO, "auto": RESIDUAL_AUTO, "f32": RESIDUAL_F32, "split": RESIDUAL_SPLIT,
+                  "bf16": RESIDUAL_BF16}
 PROFILE_KINDS = 9
 ERROR_NAMES = {-1: "TTASR_E_ARG", -2: "TTASR_E_SHAPE", -3: "TTASR_E_ARCH", -4: "TTASR_E_CUDA", -5: "TTASR_E_NOMEM"}
 
@@ -56,6 +59,7 @@ PROTOTYPES = {
                                    C.c_void_p]),
     "ttasr_ingest_destroy": (None, [C.c_void_p]),
     "ttasr_encoder_create": (C.c_int, [C.POINTER(EncoderCfg), C.POINTER(Weights), C.POINTER(C.c_void_p)]),
+    "ttasr_encoder_create_ex": (C.c_int, [C.POINTER(EncoderCfg), C.POINTER(Weights), C.c_int, C.POINTER(C.c_void_p)]),
     "ttasr_encoder_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_size_t)]),
     "ttasr_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_size_t,
                                         C.c_void_p, C.c_int, C.c_void_p]),
@@ -66,6 +70,10 @@ PROTOTYPES = {
     "ttasr_encoder_destroy": (None, [C.c_void_p]),
     "ttasr_op_gemm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                 C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "ttasr_op_gemm_split": (C.c_int, [C.c_void_p] * 8 + [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p]),
+    "ttasr_op_gemm_lnfold": (C.c_int, [C.c_void_p] * 5 + [C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                       C.c_float, C.c_int, C.c_void_p]),
+    "ttasr_op_conv_stem": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int] + [C.c_void_p] * 8),
     "ttasr_op_layernorm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                      C.c_void_p]),
     "ttasr_op_attention": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]),

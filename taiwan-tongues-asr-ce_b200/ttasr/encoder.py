@@ -76,8 +76,15 @@ def _strip_prefix(sd: dict) -> dict:
 class B200WhisperEncoder:
     main_input_name = "input_features"
 
-    def __init__(self, config, state_dict: dict, device=None):
+    def __init__(self, config, state_dict: dict, device=None, residual: str | None = None):
+        """`residual`: how the residual stream is held between the blocks — "split" (library default: bf16 hi + lo
+        pair, LayerNorms folded into the QKV / fc1 GEMMs), "f32" (fp32 stream + LayerNorm kernels), "bf16" (hi only),
+        or None = the TTASR_RESIDUAL environment variable, else the default (include/ttasr_abi.h)."""
         import torch
+
+        if residual not in _lib.RESIDUAL_MODES:
+            raise _lib.TtasrError(-1, f"residual must be one of 'f32', 'split', 'bf16' or None (got {residual!r})")
+        self.residual = residual
 
         self.config = EncoderConfig.from_any(config)
         c = self.config
@@ -126,7 +133,8 @@ class B200WhisperEncoder:
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
-            _lib.check(_lib.lib().ttasr_encoder_create(C.byref(cfg), C.byref(w), C.byref(h)))
+            _lib.check(_lib.lib().ttasr_encoder_create_ex(C.byref(cfg), C.byref(w), _lib.RESIDUAL_MODES[residual],
+                                                          C.byref(h)))
         self._handle = h
         del keep
         self._ws = None
@@ -143,10 +151,10 @@ class B200WhisperEncoder:
                 pass
 
     @classmethod
-    def from_hf(cls, model, device=None) -> "B200WhisperEncoder":
+    def from_hf(cls, model, device=None, residual=None) -> "B200WhisperEncoder":
         """Build from a Hugging Face WhisperEncoder / WhisperModel / WhisperForConditionalGeneration."""
         enc = model.get_encoder() if hasattr(model, "get_encoder") else model
-        return cls(EncoderConfig.from_any(enc.config), enc.state_dict(), device=device)
+        return cls(EncoderConfig.from_any(enc.config), enc.state_dict(), device=device, residual=residual)
 
     # ------------------------------------------------------------------ per-stage timing (bench / profiling)
     def profile(self, on: bool = True) -> None:

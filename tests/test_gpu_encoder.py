@@ -306,35 +306,39 @@ def test_graph_buckets_survive_workspace_growth(cuda_device):
 
 
 @pytest.mark.parametrize("arch_name", ["micro", "tiny"])
-def test_layernorm_fused_mode_matches_oracle(cuda_device, arch_name, monkeypatch):
-    """Opt-in TTASR_FUSE_LN=1: the per-layer LayerNorms are folded into the QKV / fc1 GEMMs (statistics and a bf16 copy
-    of the residual stream emitted by the residual GEMMs' epilogues).  Same tolerance as the default path, and the
-    two paths agree with each other far inside it."""
+def test_residual_modes_match_oracle_and_each_other(cuda_device, arch_name):
+    """The three representations of the residual stream (include/ttasr_abi.h: split = default, f32, bf16).  `split`
+    folds the per-layer LayerNorms into the QKV / fc1 GEMMs (statistics emitted by the residual GEMMs' epilogues), so it
+    launches two kernels fewer per layer; it and `f32` meet the same gate and agree with each other far inside it."""
     import torch
+    from ttasr import B200WhisperEncoder
 
-    arch, w, enc_plain = _build(arch_name)
-    monkeypatch.setenv("TTASR_FUSE_LN", "1")
-    _, _, enc_fused = _build(arch_name)
-    monkeypatch.delenv("TTASR_FUSE_LN")
-    assert enc_fused.launches_per_forward == enc_plain.launches_per_forward - 2 * arch.layers
+    arch = OE.ARCHS[arch_name]
+    w = OE.round_weights_bf16(OE.init_weights(arch, seed=0, ln_jitter=0.02))
+    enc = {m: B200WhisperEncoder(_cfg(arch), w, residual=m) for m in ("split", "f32", "bf16")}
+    assert enc["split"].launches_per_forward == enc["f32"].launches_per_forward - 2 * arch.layers
+    assert enc["bf16"].launches_per_forward == enc["split"].launches_per_forward
     feats = np.stack([OF.log_mel(OF.synth_noise(31), arch.n_mels), OF.log_mel(OF.synth_tones(32), arch.n_mels),
                       OF.log_mel(OF.pad_or_trim(OF.synth_short()), arch.n_mels)])
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
-    got = enc_fused.encode(feats, out_dtype=torch.float32)
-    _check(got.cpu().numpy(), ref)
-    plain = enc_plain.encode(feats, out_dtype=torch.float32)
-    s = OE.parity_stats(got.cpu(), plain.cpu())
+    out = {m: e.encode(feats, out_dtype=torch.float32) for m, e in enc.items()}
+    for m in ("split", "f32"):
+        print(arch_name, m, _check(out[m].cpu().numpy(), ref))
+    print(arch_name, "bf16", OE.parity_stats(out["bf16"].cpu(), ref))
+    s = OE.parity_stats(out["split"].cpu(), out["f32"].cpu())
     assert s["max_abs"] <= 0.05 and s["cosine"] >= 0.99995, s
-    assert torch.equal(got, enc_fused.encode(feats, out_dtype=torch.float32))      # deterministic
-    assert torch.equal(got[1], enc_fused.encode(feats[1:2], out_dtype=torch.float32)[0])  # batch-invariant
+    for m, e in enc.items():
+        assert torch.equal(out[m], e.encode(feats, out_dtype=torch.float32)), m             # deterministic
+        assert torch.equal(out[m][1], e.encode(feats[1:2], out_dtype=torch.float32)[0]), m  # batch-invariant
 
 
-@pytest.mark.parametrize("fused", [False, True])
-def test_residual_stream_with_outlier_channels_and_offset(cuda_device, fused, monkeypatch):
+@pytest.mark.parametrize("residual", ["f32", "split"])
+def test_residual_stream_with_outlier_channels_and_offset(cuda_device, residual):
     """Pre-trained Whisper encoders carry a few massive-activation channels and non-trivial LayerNorm gains; random
     init has neither.  Emulate them: two positional channels pinned at +40 / -25, a +1.5 offset on every channel (a
     token mean larger than the token's ordinary spread), LayerNorm gains in [0.5, 2] and biases ~0.3.  Both the
-    default path and the LayerNorm-fused one must stay inside the stated tolerance against the fp32 oracle."""
+    fp32 stream and the default split stream (which rounds x to bf16 BEFORE normalising) must stay inside the stated
+    tolerance against the fp32 oracle."""
     import torch
     from ttasr import B200WhisperEncoder
 
@@ -352,11 +356,9 @@ def test_residual_stream_with_outlier_channels_and_offset(cuda_device, fused, mo
         elif k.endswith("layer_norm.bias"):
             w[k] = 0.3 * torch.randn(arch.d_model, generator=g)
     w = OE.round_weights_bf16(w)
-    if fused:
-        monkeypatch.setenv("TTASR_FUSE_LN", "1")
-    enc = B200WhisperEncoder(_cfg(arch), w)
+    enc = B200WhisperEncoder(_cfg(arch), w, residual=residual)
     feats = np.stack([OF.log_mel(OF.synth_noise(41), arch.n_mels), OF.log_mel(OF.synth_tones(42), arch.n_mels)])
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
     got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
     s = _check(got, ref)
-    print(f"outlier/offset stream, fused={fused}: {s}")
+    print(f"outlier/offset stream, residual={residual}: {s}")

@@ -122,3 +122,126 @@ def test_bad_arguments_surface_as_errors(cuda_device):
         L.check(L.lib().ttasr_op_gemm(a.data_ptr(), a.data_ptr(), None, None, a.data_ptr(), 128, 100, 64, 0, 0, 0, None))
     with pytest.raises(L.TtasrError):
         L.check(L.lib().ttasr_op_gemm(None, a.data_ptr(), None, None, a.data_ptr(), 128, 128, 64, 0, 0, 0, None))
+
+
+# ------------------------------------------------------------------ split residual stream + folded LayerNorm
+def _split(x):
+    import torch
+
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+SPLIT_SHAPES = [(128, 128, 64), (300, 384, 384), (1500, 1280, 1280), (777, 256, 512)]
+
+
+@pytest.mark.parametrize("with_lo", [True, False], ids=["hi+lo", "hi"])
+@pytest.mark.parametrize("M,N,K", SPLIT_SHAPES, ids=[f"m{m}n{n}k{k}" for m, n, k in SPLIT_SHAPES])
+@pytest.mark.parametrize("cta_group", [1, 2], ids=["cg1", "cg2"])
+def test_gemm_split_residual(cuda_device, cta_group, M, N, K, with_lo):
+    """x' = a w^T + b + (hi + lo) -> (hi', lo') in place, plus the per-64-column (mean, M2) partials of hi'.  The
+    stream carries a +100 offset (spread 1) so a naive E[x^2] - mean^2 would lose every digit of the variance."""
+    import torch
+
+    L = _lib()
+    g = torch.Generator(device=cuda_device).manual_seed(M + N + K)
+    a = (torch.randn((M, K), generator=g, device=cuda_device) * 0.5).to(torch.bfloat16)
+    w = (torch.randn((N, K), generator=g, device=cuda_device) * (K ** -0.5)).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g, device=cuda_device)
+    x = torch.randn((M, N), generator=g, device=cuda_device) + 100.0
+    hi, lo = _split(x)
+    x_in = hi.float() + (lo.float() if with_lo else 0.0)
+    ref = a.float() @ w.float().t() + bias + x_in
+    stats = torch.full((M, N // 64, 2), float("nan"), device=cuda_device)
+    L.check(L.lib().ttasr_op_gemm_split(a.data_ptr(), w.data_ptr(), bias.data_ptr(), hi.data_ptr(),
+                                        lo.data_ptr() if with_lo else None, hi.data_ptr(),
+                                        lo.data_ptr() if with_lo else None, stats.data_ptr(), M, N, K, 0, cta_group,
+                                        _stream(torch, cuda_device)))
+    torch.cuda.synchronize()
+    ref_hi = ref.to(torch.bfloat16)
+    # hi' is the bf16 rounding of the fp32 sum (ties may fall either way on accumulation-order noise)
+    assert (hi.float() - ref).abs().max().item() <= 0.51 * 0.5 + 2e-3     # bf16 spacing at ~100 is 0.5
+    assert (hi != ref_hi).float().mean().item() < 0.02
+    if with_lo:
+        assert ((hi.float() + lo.float()) - ref).abs().max().item() <= 6e-3   # 16 mantissa bits at ~100
+    parts = hi.float().view(M, N // 64, 64)
+    mean_ref = parts.mean(dim=2)
+    m2_ref = ((parts - mean_ref[..., None]) ** 2).sum(dim=2)
+    assert (stats[..., 0] - mean_ref).abs().max().item() <= 1e-3
+    assert ((stats[..., 1] - m2_ref).abs() / (m2_ref + 1.0)).max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("act", [0, 1], ids=["id", "gelu"])
+@pytest.mark.parametrize("M,N,K", [(300, 384, 384), (1500, 3840, 1280), (200, 512, 128)],
+                         ids=["m300n384k384", "m1500n3840k1280", "m200n512k128"])
+def test_gemm_with_folded_layernorm(cuda_device, M, N, K, act):
+    """LayerNorm(x) W^T + b computed on the un-normalised bf16 rows: gamma folded into W, mean / rstd applied in the
+    epilogue from the (mean, M2) partials the split residual GEMM writes.  Control: fp32 torch LayerNorm + matmul."""
+    import torch
+
+    L = _lib()
+    g = torch.Generator(device=cuda_device).manual_seed(M * 3 + N + K)
+    x = (torch.randn((M, K), generator=g, device=cuda_device) * 2.0 + 3.0).to(torch.bfloat16)
+    x[:, 5] = 40.0
+    W = (torch.randn((N, K), generator=g, device=cuda_device) * (K ** -0.5)).to(torch.bfloat16)
+    b = torch.randn(N, generator=g, device=cuda_device)
+    gamma = 0.5 + 1.5 * torch.rand(K, generator=g, device=cuda_device)
+    beta = 0.3 * torch.randn(K, generator=g, device=cuda_device)
+    wf = (W.float() * gamma).to(torch.bfloat16)
+    c1 = wf.float().sum(dim=1).contiguous()
+    c2 = (b + W.float() @ beta).contiguous()
+    parts = K // 64
+    xp = x.float().view(M, parts, 64)
+    mean_p = xp.mean(dim=2)
+    stats = torch.stack([mean_p, ((xp - mean_p[..., None]) ** 2).sum(dim=2)], dim=2).contiguous()
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=cuda_device)
+    L.check(L.lib().ttasr_op_gemm_lnfold(x.data_ptr(), wf.data_ptr(), c1.data_ptr(), c2.data_ptr(), stats.data_ptr(),
+                                         parts, out.data_ptr(), M, N, K, act, 1e-5, 0, _stream(torch, cuda_device)))
+    torch.cuda.synchronize()
+    ln = torch.nn.functional.layer_norm(x.float(), (K,), None, None, 1e-5)
+    ref = ln @ wf.float().t() + c2   # the same rounded W' = bf16(W * gamma) on both sides
+    if act:
+        ref = torch.nn.functional.gelu(ref)
+    err = (out.float() - ref).abs().max().item()
+    assert err <= 4e-2, f"max abs err {err}"
+    assert (out.float() - ref).abs().mean().item() <= 4e-3
+
+
+@pytest.mark.parametrize("B,T,d,n_mels", [(1, 128, 128, 80), (3, 1500, 384, 80), (2, 1500, 1280, 128)],
+                         ids=["b1t128d128", "b3t1500d384", "b2t1500d1280"])
+def test_conv_stem_against_conv1d(cuda_device, B, T, d, n_mels):
+    """a6 on its own: GELU(conv1) -> GELU(conv2, stride 2) + positions as implicit GEMMs over shifted / parity-split
+    TMA views, against F.conv1d in fp32 — with special attention to the rows at the chunk edges (t = 0 and t = T - 1),
+    where the zero padding of one chunk must not pick up its batch neighbour's frames."""
+    import torch
+    import torch.nn.functional as F
+
+    L = _lib()
+    g = torch.Generator(device=cuda_device).manual_seed(B + T + d)
+    ld = (n_mels + 7) // 8 * 8
+    feats = torch.randn((B, n_mels, 2 * T), generator=g, device=cuda_device)
+    feats[:, :, :2] += 3.0       # make the edge frames loud: a leak across the chunk boundary would show
+    feats[:, :, -2:] -= 3.0
+    tm = torch.zeros((B, 2 * T, ld), dtype=torch.bfloat16, device=cuda_device)
+    tm[:, :, :n_mels] = feats.transpose(1, 2).to(torch.bfloat16)
+    w1 = (torch.randn((d, n_mels, 3), generator=g, device=cuda_device) * (3 * n_mels) ** -0.5).to(torch.bfloat16)
+    w2 = (torch.randn((d, d, 3), generator=g, device=cuda_device) * (3 * d) ** -0.5).to(torch.bfloat16)
+    b1 = 0.1 * torch.randn(d, generator=g, device=cuda_device)
+    b2 = 0.1 * torch.randn(d, generator=g, device=cuda_device)
+    pos = torch.randn((T, d), generator=g, device=cuda_device)
+    scratch = torch.empty((B, 2 * T, d), dtype=torch.bfloat16, device=cuda_device)
+    out = torch.full((B, T, d), float("nan"), device=cuda_device)
+    L.check(L.lib().ttasr_op_conv_stem(tm.data_ptr(), ld, n_mels, B, T, d, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                       b2.data_ptr(), pos.data_ptr(), scratch.data_ptr(), out.data_ptr(),
+                                       _stream(torch, cuda_device)))
+    torch.cuda.synchronize()
+    x = tm[:, :, :n_mels].float().transpose(1, 2)
+    h1 = F.gelu(F.conv1d(x, w1.float(), b1, padding=1))
+    assert (scratch.float() - h1.transpose(1, 2)).abs().max().item() <= 3e-2
+    h1r = h1.to(torch.bfloat16).float()                      # conv2 reads conv1's bf16 output
+    ref = F.gelu(F.conv1d(h1r, w2.float(), b2, stride=2, padding=1)).transpose(1, 2) + pos
+    err = (out - ref).abs()
+    assert err.max().item() <= 2e-2, f"max abs err {err.max().item()}"
+    edge = torch.cat([err[:, :2], err[:, -2:]], dim=1)
+    assert edge.max().item() <= 2e-2, "chunk-boundary rows differ"
