@@ -75,12 +75,20 @@ TTASR_API int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_sample
 /* pcm_dev:   [batch, row_stride] samples (fp32 in [-1,1], or int16 scaled by 1/32768 in-kernel).
  * n_valid_dev: optional int32[batch]; samples at index >= n_valid[b] are taken as 0.0 and never read
  *            (right-padding to 30 s without materialising it); NULL = every row holds n_samples samples.
- * feats_dev: [batch, n_mels, n_samples/160] fp32 — required.
- * tmajor_dev: optional [batch, n_samples/160, tmajor_ld] bf16 copy (channels zero-padded to tmajor_ld, which must
+ * feats_dev: [batch, n_mels, n_samples/160] fp32 (the HF `input_features`), or NULL when only tmajor_dev is wanted
+ *            (the PCM -> hidden-state pipeline: nothing downstream reads the fp32 features).
+ * tmajor_dev: optional (required if feats_dev is NULL) [batch, n_samples/160, tmajor_ld] bf16 copy (channels zero-padded to tmajor_ld, which must
  *            be even and >= n_mels) for ttasr_encoder_forward(TTASR_FEATS_BF16_TIME_MAJOR). */
 TTASR_API int ttasr_frontend_run(const ttasr_frontend_t* h, const void* pcm_dev, int pcm_dtype, int64_t batch,
                        int64_t row_stride, const int32_t* n_valid_dev, float* feats_dev, void* tmajor_dev,
                        int tmajor_ld, void* stream);
+/* The same with the dynamic-range clamp as a parameter: the reference's `max(x, x.max() - 8.0)` per chunk
+ * (feature_extraction_whisper.py:129) is clamp_decades = 8; +INFINITY writes the unclamped (log10(max(mel, 1e-10)) + 4) / 4
+ * so that a caller with a different maximum (faster-whisper takes it over the whole file) can apply
+ * its own. */
+TTASR_API int ttasr_frontend_run_ex(const ttasr_frontend_t* h, const void* pcm_dev, int pcm_dtype, int64_t batch,
+                          int64_t row_stride, const int32_t* n_valid_dev, float* feats_dev, void* tmajor_dev,
+                          int tmajor_ld, float clamp_decades, void* stream);
 /* largest batch one ttasr_frontend_run call accepts (sizes the handle's scratch: per-chunk maxima, per-tile minima) */
 TTASR_API int ttasr_frontend_max_batch(const ttasr_frontend_t* h, int64_t* out);
 TTASR_API void ttasr_frontend_destroy(ttasr_frontend_t* h);
@@ -100,6 +108,15 @@ TTASR_API int ttasr_ingest_out_len(const ttasr_ingest_t* h, int64_t n_in, int64_
  * out_dev: fp32 [out_capacity], out_capacity >= out_len(n_in); samples past the resampled signal are zero-filled. */
 TTASR_API int ttasr_ingest_run(const ttasr_ingest_t* h, const void* pcm_dev, int pcm_dtype, int channels, int64_t n_in,
                      float* out_dev, int64_t out_capacity, void* stream);
+/* Building blocks of VAD-aligned chunking (long-form files: the reference runs faster-whisper with vad_filter=True,
+ * asr_core.py:159-167, api/file_asr.py:457-465, so its 30 s windows never start or end inside a word):
+ * frame_energy: db[f] = 10 log10(mean square of pcm[f*hop .. f*hop+win)) over the 16 kHz mono signal — the track the
+ *   host scans for pauses; gather_rows: out[r, :] = pcm[start[r] .. start[r]+len[r]) zero-padded to row_samples — the
+ *   ragged [n_rows, 480000] + n_valid layout ttasr_frontend_run takes.  start: int64[n_rows], len: int32[n_rows]. */
+TTASR_API int ttasr_ingest_frame_energy(const float* pcm_dev, int64_t n, int win, int hop, float* db_dev,
+                                        int64_t n_frames, void* stream);
+TTASR_API int ttasr_ingest_gather_rows(const float* pcm_dev, const int64_t* start_dev, const int32_t* len_dev,
+                                       float* out_dev, int n_rows, int row_samples, void* stream);
 TTASR_API void ttasr_ingest_destroy(ttasr_ingest_t* h);
 
 /* ------------------------------------------------------------------ Whisper encoder --------------------------*/

@@ -101,9 +101,45 @@ def gen_ingest():
     print("ingest_scipy.npz", os.path.getsize(path), "bytes")
 
 
+def gen_warmup(ref_wav="/root/reference/api/stt_streaming/warm_up.wav"):
+    """tests/golden/warm_up_excerpt.npz: 4 s (0.3 s .. 4.3 s: a spoken phrase, a 0.5 s pause, the start of the next
+    phrase) of the reference's only real audio fixture — api/stt_streaming/warm_up.wav, 44.1 kHz 16-bit stereo, the
+    file `FasterWhisperASR.warm_up` transcribes (faster_whisper_asr.py:269-294).  Its two channels are sample-identical,
+    so one is stored and the test rebuilds the interleaved stereo frames.  Plus the expected 16 kHz mono signal from
+    scipy.signal.resample_poly and the HF numpy log-mel (80 / 128 bins) of that signal, strided."""
+    import math
+    import wave
+
+    import scipy.signal
+    from transformers import WhisperFeatureExtractor
+
+    with wave.open(ref_wav, "rb") as w:
+        sr, ch = w.getframerate(), w.getnchannels()
+        frames = np.frombuffer(w.readframes(w.getnframes()), dtype="<i2").reshape(-1, ch)
+    assert (sr, ch) == (44100, 2) and np.array_equal(frames[:, 0], frames[:, 1])
+    a, b = int(0.3 * sr), int(4.3 * sr)
+    exc = frames[a:b]
+    x = exc.astype(np.float32) / np.float32(32768.0)
+    x = x.mean(axis=1, dtype=np.float32)
+    g = math.gcd(sr, 16000)
+    y = scipy.signal.resample_poly(x, 16000 // g, sr // g)[: int(math.ceil(len(x) * 16000 / sr))].astype(np.float32)
+    out = {"pcm_ch0": exc[:, 0].copy(), "sampling_rate": np.int32(sr), "channels": np.int32(ch),
+           "mono16k_sub": y[::16].copy(), "mono16k_stats": stats(y)}
+    for n_mels in (80, 128):
+        ref = WhisperFeatureExtractor(feature_size=n_mels)._np_extract_fbank_features(FE.pad_or_trim(y)[None], "cpu")[0]
+        out[f"logmel{n_mels}_sub"] = ref[:, :420:3].copy()       # the 4 s of audio are frames 0 .. 399
+        out[f"logmel{n_mels}_stats"] = stats(ref)
+    path = os.path.join(GOLDEN_DIR, "warm_up_excerpt.npz")
+    np.savez_compressed(path, **out)
+    print("warm_up_excerpt.npz", os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     if "--ingest-only" in sys.argv:
         gen_ingest()
+    elif "--warmup-only" in sys.argv:
+        gen_warmup()
     else:
         main()
         gen_ingest()
+        gen_warmup()

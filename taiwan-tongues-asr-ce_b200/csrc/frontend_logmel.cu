@@ -274,7 +274,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(acc_a));
             const float v = acc_a > kMelFloor ? fmaf(lg, kLog2ToY, 1.0f) : kYFloor;
             if (live) {
-              *out_ptr = v;
+              if (raw) *out_ptr = v;
               tmax = fmaxf(tmax, v);
               tmin = fminf(tmin, v);
             }
@@ -334,27 +334,34 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
 constexpr int kClampTiles = 8;
 __global__ void __launch_bounds__(256)
 logmel_clamp_kernel(float* __restrict__ feats, const unsigned* __restrict__ chunk_max, const float* __restrict__ tile_min,
-                    int n_frames, int n_mels, int tiles_per_chunk, __nv_bfloat16* __restrict__ tmajor, int tmajor_ld) {
+                    int n_frames, int n_mels, int tiles_per_chunk, __nv_bfloat16* __restrict__ tmajor, int tmajor_ld,
+                    float clamp_y) {
   __shared__ float tile[kMaxMels][33];
   const int b = blockIdx.y;
-  const float lo = dec_ordered(chunk_max[b]) - 2.0f;
+  const float lo = dec_ordered(chunk_max[b]) - clamp_y;   // 8 decades of log10 = 2.0 after (x + 4) / 4; +inf = no clamp
   float* base = feats + static_cast<long long>(b) * n_mels * n_frames;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   const int wpr = tmajor_ld >> 1;  // 4-byte words per bf16 row
   const int tile_end = min((blockIdx.x + 1) * kClampTiles, tiles_per_chunk);
   for (int tt = blockIdx.x * kClampTiles; tt < tile_end; ++tt) {
     const float tmin = tile_min[static_cast<long long>(b) * tiles_per_chunk + tt];
-    if (tmin >= lo) continue;                       // the common case: nothing below the clamp
     const bool unwritten = (tmin == -INFINITY);
+    if (tmin >= lo && !unwritten) continue;         // the common case: nothing below the clamp
     const int t0 = tt * kTileFrames;
     const int t = t0 + lane;
     const float fillv = fmaxf(kYFloor, lo);
     for (int m = wrp; m < n_mels; m += 8) {         // lanes = frames: 128-byte segments along time
       float v = fillv;
       if (t < n_frames) {
-        float* ptr = base + static_cast<long long>(m) * n_frames + t;
-        if (!unwritten) v = fmaxf(*ptr, lo);
-        *ptr = v;
+        if (feats) {
+          float* ptr = base + static_cast<long long>(m) * n_frames + t;
+          if (!unwritten) v = fmaxf(*ptr, lo);
+          *ptr = v;
+        } else if (!unwritten) {
+          // time-major-only run: the bf16 copy is the only output; rounding is monotone, so clamping the rounded value
+          // and rounding the bound gives bf16(max(y, lo)) exactly
+          v = fmaxf(__bfloat162float(tmajor[(static_cast<long long>(b) * n_frames + t) * tmajor_ld + m]), lo);
+        }
       }
       tile[m][lane] = v;
     }
@@ -380,7 +387,8 @@ int frontend_tiles(int n_samples) { return (n_samples / kHop + kTileFrames - 1) 
 
 cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
                           int n_mels, int batch, const FrontTables& tables, float* feats, unsigned* chunk_max,
-                          float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream) {
+                          float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream,
+                          float clamp_decades) {
   const int n_frames = n_samples / kHop;
   const int tiles_per_chunk = (n_frames + kTileFrames - 1) / kTileFrames;
   const long long total = static_cast<long long>(batch) * tiles_per_chunk;
@@ -410,7 +418,7 @@ cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride,
                                                                  chunk_max, tile_min, tmajor, tmajor_ld);
   dim3 g2((tiles_per_chunk + kClampTiles - 1) / kClampTiles, batch);
   logmel_clamp_kernel<<<g2, 256, 0, stream>>>(feats, chunk_max, tile_min, n_frames, n_mels, tiles_per_chunk, tmajor,
-                                              tmajor_ld);
+                                              tmajor_ld, clamp_decades * 0.25f);
   return cudaGetLastError();
 }
 

@@ -24,9 +24,12 @@ size_t frontend_smem_bytes();
 
 // feats: [B, n_mels, n_samples/160] fp32 (HF layout).  tmajor (optional): [B, T, tmajor_ld] bf16, zero-padded channels.
 // n_valid (optional, device): samples >= n_valid[b] are treated as zero and never read.
+// clamp_decades: the reference's max(x, x.max() - 8) range in log10 units; +infinity disables the clamp (the features
+// are then plain (log10(max(mel, 1e-10)) + 4) / 4 and the caller applies its own, e.g. faster-whisper's per-file maximum).
 cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
                           int n_mels, int batch, const FrontTables& tables, float* feats, unsigned* chunk_max,
-                          float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream);
+                          float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream,
+                          float clamp_decades = 8.0f);
 // scratch the caller provides: chunk_max[batch] (order-encoded running maxima), tile_min[batch * frontend_tiles(n_samples)]
 int frontend_tiles(int n_samples);
 

@@ -70,7 +70,53 @@ __global__ void __launch_bounds__(256) ingest_kernel(IngestPlan plan, const T* _
   }
 }
 
+// ---- energy track for VAD-aligned chunk cuts: one warp per 10 ms hop, mean square of a 20 ms window, in dB
+__global__ void __launch_bounds__(256) frame_energy_kernel(const float* __restrict__ x, long long n, int win, int hop,
+                                                           float* __restrict__ db, long long n_frames) {
+  const long long f = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (f >= n_frames) return;
+  const long long start = f * hop;
+  float s = 0.f;
+  for (int i = lane; i < win; i += 32) {
+    const long long k = start + i;
+    const float v = k < n ? __ldg(x + k) : 0.f;
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) db[f] = 10.0f * log10f(s / static_cast<float>(win) + 1e-12f);
+}
+
+// ---- ragged rows: out[r, 0 .. len[r]) = x[start[r] .. start[r] + len[r]), zero tail
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ x, const long long* __restrict__ start,
+                                                          const int* __restrict__ len, float* __restrict__ out,
+                                                          int row_samples) {
+  const int r = blockIdx.y;
+  const long long s0 = start[r];
+  const int n = len[r];
+  float* dst = out + static_cast<long long>(r) * row_samples;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_samples; i += gridDim.x * blockDim.x)
+    dst[i] = i < n ? __ldg(x + s0 + i) : 0.f;
+}
+
 }  // namespace
+
+cudaError_t launch_frame_energy(const float* x, long long n, int win, int hop, float* db, long long n_frames,
+                                cudaStream_t stream) {
+  if (n_frames <= 0) return cudaSuccess;
+  const long long blocks = (n_frames * 32 + 255) / 256;
+  frame_energy_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(x, n, win, hop, db, n_frames);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const float* x, const long long* start, const int* len, float* out, int n_rows,
+                               int row_samples, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  dim3 grid(64, n_rows);
+  gather_rows_kernel<<<grid, 256, 0, stream>>>(x, start, len, out, row_samples);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_ingest(const IngestPlan& plan, const void* pcm, int pcm_is_i16, int channels, long long n_in,
                           float* out, long long n_out, long long out_capacity, cudaStream_t stream) {

@@ -20,4 +20,11 @@ struct IngestPlan {
 cudaError_t launch_ingest(const IngestPlan& plan, const void* pcm, int pcm_is_i16, int channels, long long n_in,
                           float* out, long long n_out, long long out_capacity, cudaStream_t stream);
 
+// db[f] = 10 log10(mean(x[f*hop .. f*hop + win)^2) + 1e-12), samples past n read as 0
+cudaError_t launch_frame_energy(const float* x, long long n, int win, int hop, float* db, long long n_frames,
+                                cudaStream_t stream);
+// out[r, :] = x[start[r] .. start[r] + len[r]) followed by zeros up to row_samples
+cudaError_t launch_gather_rows(const float* x, const long long* start, const int* len, float* out, int n_rows,
+                               int row_samples, cudaStream_t stream);
+
 }  // namespace ttasr

@@ -285,17 +285,26 @@ int ttasr_frontend_max_batch(const ttasr_frontend_t* h, int64_t* out) {
 
 int ttasr_frontend_run(const ttasr_frontend_t* h, const void* pcm_dev, int pcm_dtype, int64_t batch, int64_t row_stride,
                        const int32_t* n_valid_dev, float* feats_dev, void* tmajor_dev, int tmajor_ld, void* stream) {
+  return ttasr_frontend_run_ex(h, pcm_dev, pcm_dtype, batch, row_stride, n_valid_dev, feats_dev, tmajor_dev, tmajor_ld,
+                               8.0f, stream);
+}
+
+int ttasr_frontend_run_ex(const ttasr_frontend_t* h, const void* pcm_dev, int pcm_dtype, int64_t batch, int64_t row_stride,
+                          const int32_t* n_valid_dev, float* feats_dev, void* tmajor_dev, int tmajor_ld,
+                          float clamp_decades, void* stream) {
   if (!h) return fail(TTASR_E_ARG, "frontend_run: null handle");
+  if (!(clamp_decades > 0.f)) return fail(TTASR_E_ARG, "frontend_run: clamp_decades must be positive (8 = Whisper, +inf = none)");
   if (batch < 0 || batch > h->max_batch) return fail(TTASR_E_SHAPE, "frontend_run: batch %lld outside [0, %lld]", (long long)batch, (long long)h->max_batch);
   if (batch == 0) return TTASR_OK;
-  if (!pcm_dev || !feats_dev) return fail(TTASR_E_ARG, "frontend_run: null buffer");
+  if (!pcm_dev) return fail(TTASR_E_ARG, "frontend_run: null pcm buffer");
+  if (!feats_dev && !tmajor_dev) return fail(TTASR_E_ARG, "frontend_run: give feats_dev, tmajor_dev or both");
   if (pcm_dtype != TTASR_PCM_F32 && pcm_dtype != TTASR_PCM_I16) return fail(TTASR_E_ARG, "frontend_run: bad pcm_dtype %d", pcm_dtype);
   if (!n_valid_dev && row_stride < h->n_samples) return fail(TTASR_E_SHAPE, "frontend_run: row_stride %lld < n_samples %d without n_valid", (long long)row_stride, h->n_samples);
   if (tmajor_dev && (tmajor_ld < h->n_mels || (tmajor_ld & 1))) return fail(TTASR_E_SHAPE, "frontend_run: tmajor_ld must be even and >= n_mels");
   cudaError_t e = launch_logmel(pcm_dev, pcm_dtype == TTASR_PCM_I16, row_stride, n_valid_dev, h->n_samples, h->n_mels,
                                 static_cast<int>(batch), h->tables, feats_dev, h->chunk_max, h->tile_min,
                                 static_cast<__nv_bfloat16*>(tmajor_dev), tmajor_ld, h->num_sms,
-                                static_cast<cudaStream_t>(stream));
+                                static_cast<cudaStream_t>(stream), clamp_decades);
   if (e != cudaSuccess) return fail(TTASR_E_CUDA, "frontend_run: launch failed: %s", cudaGetErrorString(e));
   return TTASR_OK;
 }
@@ -379,6 +388,25 @@ int ttasr_ingest_run(const ttasr_ingest_t* h, const void* pcm_dev, int pcm_dtype
   cudaError_t e = launch_ingest(h->plan, pcm_dev, pcm_dtype == TTASR_PCM_I16, channels, n_in, out_dev, n_out, out_capacity,
                                 static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(TTASR_E_CUDA, "ingest_run: launch failed: %s", cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+int ttasr_ingest_frame_energy(const float* pcm_dev, int64_t n, int win, int hop, float* db_dev, int64_t n_frames,
+                              void* stream) {
+  if (!pcm_dev || !db_dev) return fail(TTASR_E_ARG, "ingest_frame_energy: null buffer");
+  if (n < 0 || win <= 0 || hop <= 0 || n_frames < 0) return fail(TTASR_E_SHAPE, "ingest_frame_energy: bad sizes");
+  cudaError_t e = launch_frame_energy(pcm_dev, n, win, hop, db_dev, n_frames, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(TTASR_E_CUDA, "ingest_frame_energy: %s", cudaGetErrorString(e));
+  return TTASR_OK;
+}
+
+int ttasr_ingest_gather_rows(const float* pcm_dev, const int64_t* start_dev, const int32_t* len_dev, float* out_dev,
+                             int n_rows, int row_samples, void* stream) {
+  if (!pcm_dev || !start_dev || !len_dev || !out_dev) return fail(TTASR_E_ARG, "ingest_gather_rows: null buffer");
+  if (n_rows < 0 || n_rows > 65535 || row_samples <= 0) return fail(TTASR_E_SHAPE, "ingest_gather_rows: bad sizes");
+  cudaError_t e = launch_gather_rows(pcm_dev, reinterpret_cast<const long long*>(start_dev), len_dev, out_dev, n_rows,
+                                     row_samples, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(TTASR_E_CUDA, "ingest_gather_rows: %s", cudaGetErrorString(e));
   return TTASR_OK;
 }
 

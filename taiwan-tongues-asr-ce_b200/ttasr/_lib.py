@@ -51,12 +51,16 @@ PROTOTYPES = {
                                         C.POINTER(C.c_void_p)]),
     "ttasr_frontend_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "ttasr_frontend_run_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "ttasr_frontend_max_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "ttasr_frontend_destroy": (None, [C.c_void_p]),
     "ttasr_ingest_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "ttasr_ingest_out_len": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "ttasr_ingest_run": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_void_p]),
+    "ttasr_ingest_frame_energy": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ttasr_ingest_gather_rows": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ttasr_ingest_destroy": (None, [C.c_void_p]),
     "ttasr_encoder_create": (C.c_int, [C.POINTER(EncoderCfg), C.POINTER(Weights), C.POINTER(C.c_void_p)]),
     "ttasr_encoder_create_ex": (C.c_int, [C.POINTER(EncoderCfg), C.POINTER(Weights), C.c_int, C.POINTER(C.c_void_p)]),

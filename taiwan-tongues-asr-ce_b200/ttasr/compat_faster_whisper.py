@@ -19,25 +19,52 @@ from .feature_extractor import B200WhisperFeatureExtractor
 
 
 class FileFeatureExtractor:
-    """faster-whisper `FeatureExtractor.__call__(waveform, padding=160, chunk_length=None)` semantics."""
+    """faster-whisper `FeatureExtractor.__call__` semantics.
+
+    Assumed upstream version: faster-whisper >= 1.1.0, `__call__(waveform, padding=160, chunk_length=None)` (numpy STFT,
+    160 zero samples appended, features of the last window padded in FEATURE space by `pad_or_trim`).  Releases up to
+    1.0.3 had `__call__(waveform, padding=True, chunk_length=None)` and appended `n_samples` (30 s) of zero AUDIO: pass
+    `padding=True` (or `padding=self.n_samples`) for that scheme.  Any integer `padding` >= 0 is reproduced exactly.
+    The reference pins only `faster-whisper>=0.9.0` (requirements.txt:10), so which scheme it ran depends on the install
+    date; the package is not installable offline, hence parity with the real class is unpinned —
+    tests/test_gpu_encoder.py::test_faster_whisper_seams checks this against the oracle's restatement of both schemes,
+    and tests/test_faster_whisper_live.py against the real class whenever `import faster_whisper` works (e.g. from
+    baseline/_ref)."""
 
     def __init__(self, fe: B200WhisperFeatureExtractor):
         self.fe = fe
         self.sampling_rate = fe.sampling_rate
         self.hop_length = fe.hop_length
         self.n_fft = fe.n_fft
+        self.chunk_length = fe.chunk_length
         self.n_samples = fe.n_samples
         self.nb_max_frames = fe.nb_max_frames
         self.time_per_frame = fe.hop_length / fe.sampling_rate
 
-    def __call__(self, waveform, padding: int = 160, chunk_length=None):
+    def __call__(self, waveform, padding=160, chunk_length=None):
         import torch
 
+        if chunk_length is not None and int(chunk_length) != int(self.chunk_length):
+            # upstream resizes n_samples / nb_max_frames here; the encoder behind this object takes 3000-frame windows
+            raise NotImplementedError(f"chunk_length={chunk_length}: only the model's own {self.chunk_length} s window "
+                                      "is implemented by the B200 encoder")
         x = np.asarray(waveform, dtype=np.float32).reshape(-1)
-        if padding:
-            x = np.concatenate([x, np.zeros(padding, np.float32)])
+        pad = self.n_samples if padding is True else int(padding or 0)
+        if pad < 0:
+            raise ValueError("padding must be >= 0")
+        if pad:
+            x = np.concatenate([x, np.zeros(pad, np.float32)])
         hop, N = self.hop_length, self.n_samples
         n_frames = x.shape[0] // hop  # whole-file STFT frames minus the dropped last one
+        if n_frames == 0:
+            return np.zeros((self.fe.feature_size, 0), np.float32)
+        # The whole-file STFT reflects 200 samples at the file END; the chunk kernel only knows "zeros after n_valid".
+        # The kept frames reach at most 40 samples into that reflection, so materialise it: with padding >= 40 it is
+        # all zeros anyway (the default scheme), with less it carries real audio.
+        half = self.n_fft // 2
+        if x.shape[0] > 1:
+            refl = x[-2: -2 - half: -1] if x.shape[0] > half + 1 else np.resize(x[-2::-1], half)
+            x = np.concatenate([x, refl.astype(np.float32)])
         # A chunk row starting `lead` frames early reproduces the whole-file frames [c*F, (c+1)*F) at local indices
         # [lead, lead + F): local frames 0-1 (left reflect) and 2999 (right reflect) of an interior row are not file
         # frames, hence lead = 2 and F = 2997.  Row 0 starts at the file start, where the reflect IS the file's own.
@@ -52,14 +79,14 @@ class FileFeatureExtractor:
             rows[c, : seg.shape[0]] = seg
             lens[c] = seg.shape[0]
         dev = self.fe._torch_device()
-        # per-chunk clamp, (x + 4) / 4; the zero tail of the last row is declared as padding so its tiles skip the FFT
-        feats = self.fe.extract(torch.from_numpy(rows).to(dev), n_valid=torch.from_numpy(lens).to(dev))
-        raw = torch.as_tensor(feats) * 4.0 - 4.0                  # back to (chunk-clamped) log10
-        # the per-chunk clamp only raises values to (chunk max - 8) <= (file max - 8), so clamping again with the
-        # file maximum gives exactly the whole-file result
-        full = torch.cat([raw[c, :, leads[c]: leads[c] + F] for c in range(n_chunks)], dim=1)[:, :n_frames]
-        full = torch.maximum(full, full.max() - 8.0)
-        return ((full + 4.0) / 4.0).cpu().numpy()
+        # unclamped (log10 + 4) / 4 per chunk (the zero tail of the last row is declared as padding so its tiles skip the
+        # FFT); the clamp is then taken over the frames of the FILE, as faster-whisper does — not per 30 s chunk, and
+        # not over the helper frames of the rows (leads, reflection) that are cut away here
+        feats = self.fe.extract(torch.from_numpy(rows).to(dev), n_valid=torch.from_numpy(lens).to(dev),
+                                clamp_decades=float("inf"))
+        full = torch.cat([feats[c, :, leads[c]: leads[c] + F] for c in range(n_chunks)], dim=1)[:, :n_frames]
+        full = torch.maximum(full, full.max() - 2.0)              # 8 decades of log10 after the (x + 4) / 4 map
+        return full.cpu().numpy()
 
 
 def patch_model(model, encoder: B200WhisperEncoder, fe: B200WhisperFeatureExtractor | None = None, wrap=None):

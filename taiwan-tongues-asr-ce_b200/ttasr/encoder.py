@@ -222,6 +222,9 @@ class B200WhisperEncoder:
             x = _lib.require_cuda_tensor(input_features, "input_features")
             if x.dtype != torch.bfloat16 or x.dim() != 3 or x.shape[1] != t_in or x.shape[2] != time_major_ld:
                 raise _lib.TtasrError(-2, f"time-major features must be bf16 [B, {t_in}, {time_major_ld}]")
+            if x.device != self.device:
+                raise _lib.TtasrError(-1, f"time-major features live on {x.device} but this encoder's weights and "
+                                          f"workspace are on {self.device} (one encoder object per GPU)")
             layout, ld = _lib.FEATS_BF16_TIME_MAJOR, time_major_ld
         B = x.shape[0]
         with torch.cuda.device(self.device):

@@ -58,7 +58,7 @@ class B200WhisperFeatureExtractor:
         self.nb_max_frames = self.n_samples // hop_length
         self.mel_filters = mel.slaney_mel_filters(feature_size, n_fft, sampling_rate)
         self._device = device
-        self._handle = None
+        self._handles = {}   # CUDA device index -> native handle (tables and scratch live on that device)
         self._extra = kwargs
 
     # ------------------------------------------------------------------ native handle
@@ -72,41 +72,52 @@ class B200WhisperFeatureExtractor:
             raise _lib.TtasrError(-3, f"device {dev} is not a CUDA device: the B200 front end has no CPU fallback")
         return dev
 
-    def _native(self):
-        if self._handle is None:
-            import torch
+    def _native(self, dev=None):
+        """The native front end of `dev` (default: this object's device).  One handle per device: its tables and
+        per-call scratch are device memory, and a handle must not be shared by concurrent streams (ttasr_abi.h) — this
+        wrapper is single-stream per device."""
+        import torch
 
+        dev = self._torch_device() if dev is None else torch.device(dev)
+        if dev.type != "cuda":
+            raise _lib.TtasrError(-3, f"device {dev} is not a CUDA device: the B200 front end has no CPU fallback")
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        h = self._handles.get(idx)
+        if h is None:
             lib = _lib.lib()
-            dev = self._torch_device()
             filt = np.ascontiguousarray(self.mel_filters, dtype=np.float32)
             win = np.ascontiguousarray(mel.periodic_hann(self.n_fft), dtype=np.float32)
             h = C.c_void_p()
-            with torch.cuda.device(dev):
+            with torch.cuda.device(idx):
                 _lib.check(lib.ttasr_frontend_create(self.feature_size, self.n_fft, self.hop_length, self.n_samples,
                                                      filt.ctypes.data, win.ctypes.data, C.byref(h)))
-            self._handle = h
-            self._handle_device = dev
-        return self._handle
+            self._handles[idx] = h
+        return h
 
     def __del__(self):
-        h, self._handle = getattr(self, "_handle", None), None
-        if h is not None:
+        handles, self._handles = getattr(self, "_handles", {}), {}
+        for h in handles.values():
             try:
                 _lib.lib().ttasr_frontend_destroy(h)
             except Exception:
                 pass
 
     # ------------------------------------------------------------------ batched device fast path
-    def extract(self, pcm, n_valid=None, return_time_major: bool = False):
+    def extract(self, pcm, n_valid=None, return_time_major: bool = False, features: bool = True,
+                clamp_decades: float = 8.0):
         """pcm: CUDA tensor [B, >= n_samples] float32 (in [-1, 1]) or int16 -> float32 [B, feature_size, 3000] (CUDA).
 
         n_valid: optional int32 CUDA tensor [B]; samples from n_valid[b] on count as zero padding and are not read
         (rows may then be shorter than 30 s).  return_time_major additionally returns the bf16 [B, 3000, ld] copy the
-        encoder's conv stem consumes directly."""
+        encoder's conv stem consumes directly; with features=False (and return_time_major) the fp32 `input_features`
+        are not written at all and (None, time_major) is returned — the PCM -> hidden-state pipeline's mode.
+        clamp_decades: the `max(x, x.max() - 8)` range per chunk; float("inf") returns unclamped features."""
         import torch
 
-        h = self._native()
         pcm = _lib.require_cuda_tensor(pcm, "pcm")
+        h = self._native(pcm.device)
+        if not features and not return_time_major:
+            raise _lib.TtasrError(-1, "features=False needs return_time_major=True")
         if pcm.dim() == 1:
             pcm = pcm.unsqueeze(0)
         if pcm.dim() != 2:
@@ -128,14 +139,16 @@ class B200WhisperFeatureExtractor:
         elif stride < self.n_samples:
             raise _lib.TtasrError(-2, f"rows hold {stride} samples < {self.n_samples}; pass n_valid for ragged input")
         with torch.cuda.device(pcm.device):
-            feats = torch.empty((B, self.feature_size, self.nb_max_frames), dtype=torch.float32, device=pcm.device)
+            feats = torch.empty((B, self.feature_size, self.nb_max_frames), dtype=torch.float32,
+                                device=pcm.device) if features else None
             tm, ld = None, 0
             if return_time_major:
                 ld = (self.feature_size + 7) // 8 * 8
                 tm = torch.empty((B, self.nb_max_frames, ld), dtype=torch.bfloat16, device=pcm.device)
-            _lib.check(_lib.lib().ttasr_frontend_run(
-                h, pcm.data_ptr(), dtype, B, stride, nv_ptr, feats.data_ptr(), tm.data_ptr() if tm is not None else None,
-                ld, _lib.current_stream_ptr(pcm.device)))
+            _lib.check(_lib.lib().ttasr_frontend_run_ex(
+                h, pcm.data_ptr(), dtype, B, stride, nv_ptr, feats.data_ptr() if feats is not None else None,
+                tm.data_ptr() if tm is not None else None,
+                ld, float(clamp_decades), _lib.current_stream_ptr(pcm.device)))
         return (feats, tm) if return_time_major else feats
 
     # ------------------------------------------------------------------ the reference's call surface
@@ -153,6 +166,8 @@ class B200WhisperFeatureExtractor:
                 f" was sampled with {self.sampling_rate} and not {sampling_rate}.")
         if self.dither != 0.0:
             raise NotImplementedError("dither != 0 is not implemented by the B200 front end")
+        if return_attention_mask is None:
+            return_attention_mask = self.return_attention_mask
         if padding not in ("max_length", True) or not truncation or pad_to_multiple_of is not None or (
                 max_length not in (None, self.n_samples)):
             raise NotImplementedError(

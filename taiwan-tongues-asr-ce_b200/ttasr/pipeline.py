@@ -12,6 +12,45 @@ from .encoder import B200WhisperEncoder
 from .feature_extractor import B200WhisperFeatureExtractor
 
 
+class PinnedStaging:
+    """Reusable pinned host staging for ragged int16 micro-batches: two flat buffers used alternately, each guarded by
+    the CUDA event of the last copy that read it, so the serving path pays for `cudaHostAlloc` only when a batch is
+    larger than anything seen before (never per request)."""
+
+    def __init__(self):
+        self._bufs = [None, None]
+        self._events = [None, None]
+        self._turn = 0
+
+    def rows(self, n_rows: int, width: int, dtype):
+        """A zeroed, contiguous, pinned [n_rows, width] tensor; call `.sent(stream)` after the copy is enqueued."""
+        import torch
+
+        i = self._turn
+        need = n_rows * width
+        if self._events[i] is not None:
+            self._events[i].synchronize()        # normally long complete: two batches ago
+        buf = self._bufs[i]
+        if buf is None or buf.numel() < need or buf.dtype != dtype:
+            grow = max(need, 2 * buf.numel() if buf is not None and buf.dtype == dtype else need)
+            buf = torch.empty(grow, dtype=dtype).pin_memory()
+            self._bufs[i] = buf
+        view = buf[:need].view(n_rows, width)
+        view.zero_()
+        return view
+
+    def sent(self, device=None):
+        import torch
+
+        if device is not None and torch.device(device).type != "cuda":   # host-only pipelines (tests): nothing in flight
+            self._turn ^= 1
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self._events[self._turn] = ev
+        self._turn ^= 1
+
+
 class B200LogMelEncoder:
     def __init__(self, feature_extractor: B200WhisperFeatureExtractor, encoder: B200WhisperEncoder):
         if feature_extractor.feature_size != encoder.config.num_mel_bins:
@@ -29,12 +68,15 @@ class B200LogMelEncoder:
 
     def encode_device(self, pcm, n_valid=None, out_dtype=None):
         """pcm: CUDA [B, n_samples] float32 / int16 -> [B, 1500, d] CUDA."""
-        _, tm = self.feature_extractor.extract(pcm, n_valid=n_valid, return_time_major=True)
+        # only the bf16 time-major tensor the conv stem reads is produced: the fp32 `input_features` would be written
+        # (1.5 MB per chunk at 128 bins) and never read
+        _, tm = self.feature_extractor.extract(pcm, n_valid=n_valid, return_time_major=True, features=False)
         return self.encoder.encode(tm, out_dtype=out_dtype, time_major_ld=tm.shape[2])
 
     def encode_host(self, pcm_host, out_host=None, n_valid=None):
-        """pcm_host: CPU tensor [B, n_samples] (pinned for full-rate copies).  Returns the hidden states on the
-        host when `out_host` (a pinned CPU tensor [B, 1500, d] bf16) is given, else the CUDA tensor."""
+        """pcm_host: CPU tensor [B, n_samples] (pinned for full-rate copies).  Returns the CUDA tensor of hidden states,
+        or — when `out_host` (a pinned CPU tensor [B, 1500, d] bf16) is given — `out_host` with the device-to-host copy
+        ENQUEUED on the current stream, not complete: synchronise the stream (or the device) before reading it."""
         import torch
 
         B = pcm_host.shape[0]
@@ -89,7 +131,7 @@ class B200LogMelEncoder:
             main.wait_event(in_ready[k])
             if k >= 2 and outs is not None:
                 main.wait_event(out_ready[k - 2])  # hidden[k & 1] has been copied out before it is overwritten
-            _, tm = self.feature_extractor.extract(buf, return_time_major=True)
+            _, tm = self.feature_extractor.extract(buf, return_time_major=True, features=False)
             in_free[k].record(main)
             hidden[k & 1] = self.encoder.encode(tm, time_major_ld=tm.shape[2])
             if consume is not None:
@@ -119,6 +161,7 @@ class GraphedLogMelEncoder:
         self.buckets = tuple(sorted(set(int(b) for b in buckets)))
         self.n_samples = pipeline.feature_extractor.n_samples
         self._graphs = {}
+        self._staging = PinnedStaging()
         self._pool = None   # one memory pool for all buckets: they are replayed one at a time and the result is copied out
         self.replays = 0
         # the graphs bake the encoder's workspace address in: size it for the largest bucket before any capture
@@ -168,11 +211,13 @@ class GraphedLogMelEncoder:
             n = len(rows)
             lens = [min(int(r.numel()), self.n_samples) for r in rows] if lens is None else list(lens)
             width = (max(max(lens), 1) + 7) // 8 * 8
-            host = torch.zeros((n, width), dtype=torch.int16).pin_memory()
+            host = self._staging.rows(n, width, torch.int16)
             for i, r in enumerate(rows):
                 host[i, : lens[i]] = r[: lens[i]]
+            staged = True
         else:
             host = rows
+            staged = False
             n, width = host.shape
             lens = [min(width, self.n_samples)] * n if lens is None else list(lens)
         if n == 0:
@@ -185,6 +230,8 @@ class GraphedLogMelEncoder:
             self._ws_generation = gen
         graph, pcm, n_valid, hidden = self._graphs.get(bucket) or self._build(bucket)
         pcm[:n, :width].copy_(host[:, :width], non_blocking=True)
+        if staged:
+            self._staging.sent(self.pipeline.device)
         nv = torch.zeros((bucket,), dtype=torch.int32)
         nv[:n] = torch.tensor(lens, dtype=torch.int32)
         n_valid.copy_(nv, non_blocking=False)

@@ -362,3 +362,88 @@ def test_residual_stream_with_outlier_channels_and_offset(cuda_device, residual)
     got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
     s = _check(got, ref)
     print(f"outlier/offset stream, residual={residual}: {s}")
+
+
+def test_plugin_is_constructible_from_the_factory_kwargs(cuda_device, tmp_path):
+    """`ASRFactory.create_asr_pipeline(type, model_size=...)` -> `Plugin(**kwargs)` (asr_factory.py:9-30,
+    streaming_asr.py:116-121): B200ASR resolves `<root>/<model_size>` like faster_whisper_asr.py:24-49, loads the
+    encoder from the CTranslate2 `model.bin` found there, warms up on a 44.1 kHz stereo WAV like :269-294, splits a
+    buffer longer than 30 s into windows instead of truncating it, and runs decode_fn off the event loop."""
+    import asyncio
+    import threading
+    import types
+    import wave
+    import torch
+    from test_model_dir import ct2_variables_from_hf, write_ct2_model_bin
+    from ttasr.asr_plugin import B200ASR
+
+    arch = OE.ARCHS["micro"]
+    w = OE.round_weights_bf16(OE.init_weights(arch, seed=0, ln_jitter=0.02))
+    mdir = tmp_path / "my-whisper-ct2"
+    mdir.mkdir()
+    write_ct2_model_bin(str(mdir / "model.bin"), ct2_variables_from_hf(w, arch, "float16"))
+    (mdir / "config.json").write_text("{}")
+    (mdir / "tokenizer.json").write_text("{}")
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "warm_up_excerpt.npz"))
+    wav = tmp_path / "warm_up.wav"
+    with wave.open(str(wav), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(int(g["sampling_rate"]))
+        f.writeframes(np.stack([g["pcm_ch0"]] * 2, axis=1).astype("<i2").tobytes())
+
+    loop_thread = threading.get_ident()
+    seen = []
+
+    def decode(hidden, info):
+        seen.append((tuple(hidden.shape), info["n_samples"], threading.get_ident()))
+        return {"text": "好", "words": []}
+
+    with pytest.raises(FileNotFoundError):
+        B200ASR(model_size="no-such-model", model_root=str(tmp_path), decode_fn=decode)
+    asr = B200ASR.from_kwargs(model_size="my-whisper-ct2", model_root=str(tmp_path), decode_fn=decode,
+                              warm_up_wav=str(wav), batch_window_s=0.01)
+    assert asr.weights_format == "ct2" and asr.model_path == str(mdir) and asr.model_size == "my-whisper-ct2"
+    info = asr.warm_up()
+    assert info["orig_sr"] == 44100 and info["channels"] == 2 and info["chunks"] == 1 and 3.9 < info["seconds"] < 4.1
+    # fp16 storage of bf16-representable weights is exact: the plugin's encoder equals one built from the HF names
+    rng = np.random.default_rng(12)
+    long_pcm = (rng.standard_normal(16000 * 41) * 2500).astype("<i2")     # 41 s: two windows
+    client = types.SimpleNamespace(scratch_buffer=bytearray(long_pcm.tobytes()), samples_width=2, last_start_time=1.5,
+                                   client_id=0)
+    out = asyncio.run(asr.transcribe(client))
+    assert out["text"] == "好" and out["final"] and abs(out["duration"] - 41.0) < 1e-6
+    shape, n, tid = seen[-1]
+    assert shape == (2, 1500, arch.d_model) and n == len(long_pcm) and tid != loop_thread
+    feats = np.stack([OF.log_mel(long_pcm[:480000].astype(np.float32) / 32768.0, arch.n_mels),
+                      OF.log_mel(OF.pad_or_trim(long_pcm[480000:].astype(np.float32) / 32768.0), arch.n_mels)])
+    ref = OE.encoder_forward(torch.from_numpy(feats), w, arch)
+    hidden = asr.pipeline.encode_device(
+        torch.from_numpy(np.stack([long_pcm[:480000], np.pad(long_pcm[480000:], (0, 480000 - (len(long_pcm) - 480000)))])
+                         ).to(cuda_device),
+        n_valid=torch.tensor([480000, len(long_pcm) - 480000], dtype=torch.int32, device=cuda_device))
+    _check(hidden.float().cpu().numpy(), ref.numpy())
+    # without a decoder and without a Hugging Face directory there is nothing to decode with: say so at construction
+    with pytest.raises(Exception):
+        B200ASR(model_size="my-whisper-ct2", model_root=str(tmp_path))
+
+
+def test_faster_whisper_padding_schemes(cuda_device):
+    """Both upstream padding schemes (>= 1.1.0: 160 zero samples; <= 1.0.3: 30 s of zero audio) and padding=0, whose
+    last frames reach into the whole-file reflection — all against the oracle's whole-file log-mel with the global clamp."""
+    from ttasr import B200WhisperFeatureExtractor
+    from ttasr.compat_faster_whisper import FileFeatureExtractor
+
+    ffe = FileFeatureExtractor(B200WhisperFeatureExtractor(feature_size=80))
+    assert ffe.chunk_length == 30 and ffe.nb_max_frames == 3000
+    rng = np.random.default_rng(6)
+    wave_ = (0.1 * rng.standard_normal(16000 * 33 + 91)).astype(np.float32)
+    wave_[-400:] *= 8.0                                    # loud file end: the reflection matters for padding < 40
+    for padding, n_pad in ((160, 160), (True, 480000), (0, 0), (17, 17)):
+        got = ffe(wave_, padding=padding)
+        padded = np.concatenate([wave_, np.zeros(n_pad, np.float32)])
+        ref = OF.log_mel_unclamped(padded, 80)[:, :-1]
+        ref = (np.maximum(ref, ref.max() - 8.0) + 4.0) / 4.0
+        assert got.shape == ref.shape, (padding, got.shape, ref.shape)
+        assert np.abs(got - ref).max() <= 1e-4, padding
+    with pytest.raises(NotImplementedError):
+        ffe(wave_, chunk_length=20)
+    assert ffe(np.zeros(100, np.float32), padding=0).shape == (80, 0)

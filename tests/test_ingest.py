@@ -92,3 +92,81 @@ def test_ingest_bad_arguments(cuda_device):
         ing.load(torch.zeros((10, 9), dtype=torch.int16, device=cuda_device))
     with pytest.raises(ValueError):
         B200AudioIngest(44100.5)
+
+
+# ------------------------------------------------------------------ real audio + pause-aligned chunking (round 2)
+def _warm_up_excerpt():
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "warm_up_excerpt.npz"))
+    ch0 = g["pcm_ch0"]
+    frames = np.stack([ch0, ch0], axis=1)           # the reference file's two channels are sample-identical
+    return g, frames, int(g["sampling_rate"])
+
+
+@pytest.mark.gpu
+def test_real_audio_warm_up_wav_through_ingest_and_front_end(cuda_device):
+    """The reference's only real recording (api/stt_streaming/warm_up.wav, 44.1 kHz stereo; faster_whisper_asr.py:
+    279-294) -> B200AudioIngest (mono mix, 160/441 polyphase resampling, chunking) -> log-mel, against scipy
+    resample_poly and the HF numpy extractor: live when they import, and against the committed golden samples."""
+    import torch
+    from ttasr import B200AudioIngest, B200WhisperFeatureExtractor
+
+    g, frames, sr = _warm_up_excerpt()
+    chunks, n_valid = B200AudioIngest(sr).load(torch.from_numpy(frames).to(cuda_device))
+    n = int(n_valid[0])
+    assert chunks.shape == (1, 480000) and n == int(np.ceil(frames.shape[0] * 16000 / sr))
+    y = chunks[0, :n].cpu().numpy()
+    assert np.abs(y[::16] - g["mono16k_sub"]).max() <= 2e-6
+    assert abs(float(y.astype(np.float64).sum()) - float(g["mono16k_stats"][0])) <= 1e-3
+    assert float(chunks[0, n:].abs().max()) == 0.0
+    for n_mels in (80, 128):
+        feats = B200WhisperFeatureExtractor(feature_size=n_mels).extract(chunks, n_valid=n_valid)[0].cpu().numpy()
+        assert np.abs(feats[:, :420:3] - g[f"logmel{n_mels}_sub"]).max() <= 1e-4
+        assert abs(float(feats.astype(np.float64).sum()) - float(g[f"logmel{n_mels}_stats"][0])) <= 1e-4 * feats.size
+    # live against the oracle chain (numpy log-mel of the scipy-resampled signal)
+    from oracle import frontend as OF
+    from oracle import ingest as OI
+
+    ref_y = OI.load_like_librosa(frames, sr)
+    assert np.abs(y - ref_y).max() <= 2e-6
+    ref = OF.log_mel(OF.pad_or_trim(ref_y), 128)
+    feats = B200WhisperFeatureExtractor(feature_size=128).extract(chunks, n_valid=n_valid)[0].cpu().numpy()
+    assert np.abs(feats - ref).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_pause_aligned_chunks_on_real_speech(cuda_device):
+    """Long-form ingest (BASELINE.json configs[3]): the excerpt tiled to ~100 s; every cut of `load_aligned` must fall
+    into one of the recording's pauses (or be a 30 s hard cut when a window holds none), chunks tile the signal, and
+    each row is the corresponding slice of the flat 16 kHz signal, zero padded."""
+    import torch
+    from ttasr import B200AudioIngest
+
+    _, frames, sr = _warm_up_excerpt()
+    long = np.concatenate([frames] * 25)              # 100 s, a 0.5 s pause every 4 s
+    ing = B200AudioIngest(sr)
+    dev_frames = torch.from_numpy(long).to(cuda_device)
+    flat = ing.load(dev_frames, pad_to_chunks=False)
+    chunks, n_valid, starts = ing.load_aligned(dev_frames)
+    n = int(flat.shape[0])
+    lens = n_valid.cpu().numpy().astype(np.int64)
+    st = starts.numpy()
+    assert st[0] == 0 and (st[1:] == (st[:-1] + lens[:-1])).all() and st[-1] + lens[-1] == n
+    assert lens.max() <= 480000 and len(lens) == 4    # 100 s in <= 30 s pieces cut at pauses
+    flat_np = flat.cpu().numpy()
+    rows = chunks.cpu().numpy()
+    for r in range(len(lens)):
+        assert np.array_equal(rows[r, : lens[r]], flat_np[st[r]: st[r] + lens[r]])
+        assert not rows[r, lens[r]:].any()
+    # interior cuts sit in quiet audio: the 100 ms around each one is at least 25 dB under the recording's loud parts
+    loud = 10 * np.log10(np.percentile(flat_np ** 2, 99) + 1e-12)
+    for c in st[1:]:
+        seg = flat_np[c - 800: c + 800]
+        assert 10 * np.log10((seg ** 2).mean() + 1e-12) <= loud - 25.0, c
+    # caller-supplied cut list (e.g. from the host's own VAD) and its validation
+    chunks2, nv2, st2 = ing.load_aligned(dev_frames, cut_points=[(0, 160000), (160000, 400000)])
+    assert chunks2.shape == (2, 480000) and nv2.tolist() == [160000, 240000]
+    assert np.array_equal(chunks2[1, :240000].cpu().numpy(), flat_np[160000:400000])
+    with pytest.raises(ValueError):
+        ing.load_aligned(dev_frames, cut_points=[(0, 480001)])
