@@ -116,6 +116,44 @@ __device__ __forceinline__ void mask_tail(uint32_t (&v)[32], int col0, int valid
 #ifndef TTASR_ATTN_F32X2
 #define TTASR_ATTN_F32X2 1
 #endif
+#ifndef TTASR_ATTN_SETMAXNREG
+#define TTASR_ATTN_SETMAXNREG 0
+#endif
+#ifndef TTASR_ATTN_POLY_Q0
+#define TTASR_ATTN_POLY_Q0 0
+#endif
+#ifndef TTASR_ATTN_POLY_Q1
+#define TTASR_ATTN_POLY_Q1 0
+#endif
+#ifndef TTASR_ATTN_POLY_Q2
+#define TTASR_ATTN_POLY_Q2 0
+#endif
+#ifndef TTASR_ATTN_POLY_Q3
+#define TTASR_ATTN_POLY_Q3 0
+#endif
+// 2^x for a PAIR on the FMA / ALU pipes instead of the 16-op/clk MUFU pipe (FlashAttention-4's trick): n = rint(x) by
+// the magic-number add, f = x - n in [-0.5, 0.5], 2^f by a degree-3 minimax polynomial (max rel err 7.6e-5 — P is
+// rounded to bf16, 3.9e-3, right after), exponent added into the bit pattern.  x <= 32 here (lazy rescale bound);
+// x is clamped at -126, where 2^x is 1e-38 and indistinguishable from 0 in the row sum.
+__device__ __forceinline__ void exp2_poly_pair(uint32_t& a, uint32_t& b) {
+  constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+  const float x0 = fmaxf(__uint_as_float(a), -126.0f), x1 = fmaxf(__uint_as_float(b), -126.0f);
+  const f32x2_t x = pack2(x0, x1);
+  const f32x2_t t = add2(x, pack2(kMagic, kMagic));
+  const f32x2_t n = add2(t, pack2(-kMagic, -kMagic));
+  const f32x2_t f = add2(x, n ^ 0x8000000080000000ull);  // x - n
+  f32x2_t p = fma2(pack2(0.05520551f, 0.05520551f), f, pack2(0.24261396f, 0.24261396f));
+  p = fma2(p, f, pack2(0.69325476f, 0.69325476f));
+  p = fma2(p, f, pack2(0.99992773f, 0.99992773f));
+  float p0, p1, t0, t1;
+  unpack2(p, p0, p1);
+  unpack2(t, t0, t1);
+  a = __float_as_uint(p0) + (__float_as_uint(t0) << 23);
+  b = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
+}
+
+// POLY8: of every 8 consecutive scores of the chunk, the first POLY8 (even) take the polynomial, the rest MUFU.EX2
+template <int POLY8>
 __device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], float m_used) {
 #if TTASR_ATTN_F32X2
   // packed FFMA2: one issue slot scales and shifts two scores (the sweep shares its scheduler with the MMA / TMA warps)
@@ -130,8 +168,12 @@ __device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], float m_used) {
         "mov.b64 {%0, %1}, t; }"
         : "+r"(v[i]), "+r"(v[i + 1])
         : "r"(__float_as_uint(kLog2e)), "r"(__float_as_uint(neg_m)));
-    v[i] = __float_as_uint(ex2(__uint_as_float(v[i])));
-    v[i + 1] = __float_as_uint(ex2(__uint_as_float(v[i + 1])));
+    if ((i & 7) < POLY8) {
+      exp2_poly_pair(v[i], v[i + 1]);
+    } else {
+      v[i] = __float_as_uint(ex2(__uint_as_float(v[i])));
+      v[i + 1] = __float_as_uint(ex2(__uint_as_float(v[i + 1])));
+    }
   }
 #else
 #pragma unroll
@@ -211,9 +253,19 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     q0 = qb * 2 * kTile;
   };
 
+  // register file: 384 threads x 168 at launch; with TTASR_ATTN_SETMAXNREG the four control warps give theirs to the two
+  // softmax warpgroups, whose 128 live scores + pipelined exp / pack state otherwise sit exactly at the 168 ceiling
+#if TTASR_ATTN_SETMAXNREG
+#define TTASR_REG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 56;")
+#define TTASR_REG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 224;")
+#else
+#define TTASR_REG_DEC()
+#define TTASR_REG_INC()
+#endif
   if (warp == 0) {
     // ===================================================== TMA producer (whole warp walks the loop, one elected
     // lane issues: uniform control flow keeps descriptors / addresses in uniform registers)
+    TTASR_REG_DEC();
     {
       int stage = 0;
       uint32_t phase = 0, qphase = 0;
@@ -248,6 +300,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     // ===================================================== MMA issuer (uniform control flow, one elected lane
     // issues: each tcgen05.mma is then a single UTCHMMA on precomputed uniform registers instead of a per-instruction
     // elect/waterfall sequence that starves behind the softmax warps of the same scheduler)
+    TTASR_REG_DEC();
     {
       constexpr uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, 0, 0);      // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = umma_idesc_bf16(kTile, kHeadDim, 0, 1);   // P (tmem)   x V (MN-major)
@@ -359,6 +412,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     }
   } else if (warp >= 4) {
     // ===================================================== softmax + output, one thread per query row
+    TTASR_REG_INC();
     const int t = (warp - 4) >> 2;          // query tile owned by this warpgroup
     const int wq = warp & 3;                // TMEM lane quarter
     const int row = wq * 32 + lane;
@@ -436,8 +490,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         // place; the row sum / bf16 packing / P store of a quarter follow the exponentials of the next one.
         uint32_t pk[16];
         float lsum = 0.f;
+        // TTASR_ATTN_POLY_Q<c>: how many of every 8 exponentials of quarter c run on the FMA pipe (polynomial)
         auto stage_a = [&](uint32_t (&v)[32], int c) {
-          exp_inplace(v, m_used);
+          if (c == 0) exp_inplace<TTASR_ATTN_POLY_Q0>(v, m_used);
+          else if (c == 1) exp_inplace<TTASR_ATTN_POLY_Q1>(v, m_used);
+          else if (c == 2) exp_inplace<TTASR_ATTN_POLY_Q2>(v, m_used);
+          else exp_inplace<TTASR_ATTN_POLY_Q3>(v, m_used);
         };
         auto stage_b = [&](const uint32_t (&v)[32], int c) {
           lsum += sum_pack(v, pk);
@@ -504,6 +562,8 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     }
     if (t == 0) asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + 0), "r"(256) : "memory");  // absorb the last token
     if (leader) tma_store_wait<0>();
+  } else {
+    TTASR_REG_DEC();  // warps 2-3: setmaxnreg is warpgroup-wide
   }
 
   tc_fence_before();

@@ -47,9 +47,6 @@ struct __align__(16) FrontSmem {
   float ti[kGroups * kTStride];    // (im);                 Z (im);       power of the odd frame
   float2 tw[kNfft];                // W400^(n2*k1) at [k1*20 + n2]
   float win[kNfft];
-  int4 mel_ops[kMaxMelOps];
-  int mel_op_off[kMelWarps + 1];
-  int mel_m0[kMelWarps + 1];
   float wmin[2][kThreads / 32];   // per-warp tile minima, double-buffered by tile parity (see the reduction)
   unsigned long long bar;
 };
@@ -78,7 +75,8 @@ constexpr float kLog2ToY = 0.25f * 0.30102999566398120f; // y = log2(p) * log10(
 template <typename T>
 __global__ void __launch_bounds__(kThreads, 2)
 logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int* __restrict__ n_valid, int n_samples,
-                     int n_frames, int n_mels, int batch, FrontTables tables, float* __restrict__ raw,
+                     int n_frames, int n_mels, int batch, FrontTables tables, const __grid_constant__ MelProgram mel,
+                     float* __restrict__ raw,
                      unsigned* __restrict__ chunk_max, float* __restrict__ tile_min, __nv_bfloat16* __restrict__ tmajor,
                      int tmajor_ld) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -93,11 +91,6 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
   for (int i = tid; i < kNfft; i += kThreads) {
     s.tw[i] = tables.twiddle[i];
     s.win[i] = tables.window[i];
-  }
-  for (int i = tid; i < kMaxMelOps; i += kThreads) s.mel_ops[i] = tables.mel_ops[i];
-  if (tid <= kMelWarps) {
-    s.mel_op_off[tid] = tables.mel_op_off[tid];
-    s.mel_m0[tid] = tables.mel_m0[tid];
   }
   const uint32_t bar = smem_u32(&s.bar);
   if (tid == 0) {
@@ -253,17 +246,17 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
       // filters and walks its frequency bins once with two accumulators (a bin feeds <= 2 adjacent triangles): the
       // program (bin, weight for the current filter, weight for the next one, filters completed) is built on the host.
       {
-        const int lane = tid & 31, wrp = tid >> 5;
+        const int lane = tid & 31;
+        const int wrp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: constant-bank indexing
         const bool live = (t0 + lane) < n_frames;
-        int m = s.mel_m0[wrp];
+        int m = mel.m0[wrp];
         float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
         __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
         const unsigned char* pw = reinterpret_cast<const unsigned char*>(&s.tr[lane]);
         float acc_a = 0.f, acc_b = 0.f;
-        const int4* op_ptr = &s.mel_ops[s.mel_op_off[wrp]];
-        const int4* const op_end = &s.mel_ops[s.mel_op_off[wrp + 1]];
-        for (; op_ptr < op_end; ++op_ptr) {
-          const int4 op = *op_ptr;
+        const int op_end = mel.op_off[wrp + 1];
+        for (int oi = mel.op_off[wrp]; oi < op_end; ++oi) {
+          const int4 op = mel.ops[oi];
           const float p = *reinterpret_cast<const float*>(pw + op.x);
           acc_a = fmaf(__int_as_float(op.y), p, acc_a);
           acc_b = fmaf(__int_as_float(op.z), p, acc_b);
@@ -386,7 +379,7 @@ size_t frontend_smem_bytes() { return sizeof(FrontSmem); }
 int frontend_tiles(int n_samples) { return (n_samples / kHop + kTileFrames - 1) / kTileFrames; }
 
 cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
-                          int n_mels, int batch, const FrontTables& tables, float* feats, unsigned* chunk_max,
+                          int n_mels, int batch, const FrontTables& tables, const MelProgram& mel, float* feats, unsigned* chunk_max,
                           float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream,
                           float clamp_decades) {
   const int n_frames = n_samples / kHop;
@@ -410,11 +403,11 @@ cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride,
   const int grid = static_cast<int>(total < 2LL * num_sms ? total : 2LL * num_sms);
   if (pcm_is_i16)
     logmel_frames_kernel<int16_t><<<grid, kThreads, smem, stream>>>(static_cast<const int16_t*>(pcm), row_stride, n_valid,
-                                                                   n_samples, n_frames, n_mels, batch, tables, feats,
+                                                                   n_samples, n_frames, n_mels, batch, tables, mel, feats,
                                                                    chunk_max, tile_min, tmajor, tmajor_ld);
   else
     logmel_frames_kernel<float><<<grid, kThreads, smem, stream>>>(static_cast<const float*>(pcm), row_stride, n_valid,
-                                                                 n_samples, n_frames, n_mels, batch, tables, feats,
+                                                                 n_samples, n_frames, n_mels, batch, tables, mel, feats,
                                                                  chunk_max, tile_min, tmajor, tmajor_ld);
   dim3 g2((tiles_per_chunk + kClampTiles - 1) / kClampTiles, batch);
   logmel_clamp_kernel<<<g2, 256, 0, stream>>>(feats, chunk_max, tile_min, n_frames, n_mels, tiles_per_chunk, tmajor,

@@ -132,6 +132,7 @@ struct ttasr_frontend {
   int n_mels = 0;
   int n_samples = 0;
   FrontTables tables{};
+  MelProgram mel{};               // host copy: passed to the frames kernel as a parameter (constant bank)
   void* table_mem = nullptr;
   unsigned* chunk_max = nullptr;  // per-chunk running maxima (order-encoded), capacity max_batch
   float* tile_min = nullptr;      // per-tile minima, capacity max_batch * tiles per chunk
@@ -247,7 +248,10 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
   h->num_sms = sms;
   h->n_mels = n_mels;
   h->n_samples = n_samples;
-  const size_t bytes = sizeof(float2) * kNfft + sizeof(int4) * kMaxMelOps + sizeof(float) * kNfft + 2 * sizeof(int) * (kMelWarps + 1);
+  memcpy(h->mel.ops, ops.data(), sizeof(int4) * kMaxMelOps);
+  memcpy(h->mel.op_off, op_off.data(), sizeof(int) * (kMelWarps + 1));
+  memcpy(h->mel.m0, warp_m0.data(), sizeof(int) * (kMelWarps + 1));
+  const size_t bytes = sizeof(float2) * kNfft + sizeof(float) * kNfft;
   cudaError_t e = cudaMalloc(&h->table_mem, bytes);
   if (e != cudaSuccess) { delete h; return fail(TTASR_E_NOMEM, "frontend_create: cudaMalloc tables: %s", cudaGetErrorString(e)); }
   char* pdev = static_cast<char*>(h->table_mem);
@@ -258,10 +262,7 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
     return dst;
   };
   h->tables.twiddle = static_cast<const float2*>(put(tw.data(), sizeof(float2) * kNfft));
-  h->tables.mel_ops = static_cast<const int4*>(put(ops.data(), sizeof(int4) * kMaxMelOps));   // 16-byte aligned
   h->tables.window = static_cast<const float*>(put(window, sizeof(float) * kNfft));
-  h->tables.mel_op_off = static_cast<const int*>(put(op_off.data(), sizeof(int) * (kMelWarps + 1)));
-  h->tables.mel_m0 = static_cast<const int*>(put(warp_m0.data(), sizeof(int) * (kMelWarps + 1)));
   h->max_batch = 1 << 14;
   if (e == cudaSuccess) e = cudaMalloc(&h->chunk_max, sizeof(unsigned) * h->max_batch);
   if (e == cudaSuccess) e = cudaMalloc(&h->tile_min, sizeof(float) * h->max_batch * frontend_tiles(n_samples));
@@ -302,7 +303,7 @@ int ttasr_frontend_run_ex(const ttasr_frontend_t* h, const void* pcm_dev, int pc
   if (!n_valid_dev && row_stride < h->n_samples) return fail(TTASR_E_SHAPE, "frontend_run: row_stride %lld < n_samples %d without n_valid", (long long)row_stride, h->n_samples);
   if (tmajor_dev && (tmajor_ld < h->n_mels || (tmajor_ld & 1))) return fail(TTASR_E_SHAPE, "frontend_run: tmajor_ld must be even and >= n_mels");
   cudaError_t e = launch_logmel(pcm_dev, pcm_dtype == TTASR_PCM_I16, row_stride, n_valid_dev, h->n_samples, h->n_mels,
-                                static_cast<int>(batch), h->tables, feats_dev, h->chunk_max, h->tile_min,
+                                static_cast<int>(batch), h->tables, h->mel, feats_dev, h->chunk_max, h->tile_min,
                                 static_cast<__nv_bfloat16*>(tmajor_dev), tmajor_ld, h->num_sms,
                                 static_cast<cudaStream_t>(stream), clamp_decades);
   if (e != cudaSuccess) return fail(TTASR_E_CUDA, "frontend_run: launch failed: %s", cudaGetErrorString(e));

@@ -1,4 +1,7 @@
-"""BASELINE.json configs[4]: the streaming server's load shape on ONE GPU — utterances of
+"""BASELINE.json configs[4]: the streaming server's load shape on one GPU, or — under
+`python -m torch.distributed.run --nproc-per-node N tools/streaming_sim.py ...` — on N GPUs of one box, one server
+process per GPU with the clients of each concurrency level dealt round-robin over the processes (what a load balancer
+in front of N single-GPU servers does; there is no cross-GPU traffic on the data path) — utterances of
 U ~ Uniform[1 s, 5 s] (int16, as they sit in client.scratch_buffer) arrive as a Poisson process from `concurrency`
 clients; B200ASR's cross-client micro-batcher (window 5 ms) encodes whatever is ready in one launch group (CUDA graph
 per batch-size bucket).  The decoder is a stub that waits for the hidden states on the GPU (decode is out of scope).
@@ -46,7 +49,12 @@ def main():
     ap.add_argument("--workload", default="large-v3")
     ap.add_argument("--eager", action="store_true")
     args = ap.parse_args()
-    dev = torch.device("cuda", 0)
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
     cfg = ttasr.EncoderConfig.named(args.workload)
     fe = ttasr.B200WhisperFeatureExtractor(feature_size=cfg.num_mel_bins)
     enc = ttasr.B200WhisperEncoder(cfg, bench.make_gpu_weights(cfg, dev))
@@ -57,11 +65,19 @@ def main():
         return {"text": "x", "words": []}
 
     out = {}
-    for conc in [int(c) for c in args.concurrency.split(",")]:
+    from ttasr.dp import gather_host
+
+    for total_conc in [int(c) for c in args.concurrency.split(",")]:
+        conc = total_conc // world + (1 if rank < total_conc % world else 0)   # this server's share of the clients
+        if world > 1:
+            dist.barrier()
+        if conc == 0:
+            gather_host(None)
+            continue
         asr = B200ASR(pipe, decode, batch_window_s=0.005, max_batch=max(conc, 1), use_graphs=not args.eager)
         asr.warm_up()
         rng = np.random.default_rng(777)
-        per_client = max(1, args.utterances // conc)
+        per_client = max(1, args.utterances // total_conc)
 
         async def warm():
             await asyncio.gather(*(client_loop(asr, i, 1, np.random.default_rng(i), [], []) for i in range(conc)))
@@ -70,20 +86,35 @@ def main():
         lat, speech = [], []
 
         async def run():
-            await asyncio.gather(*(client_loop(asr, i, per_client, np.random.default_rng(777 + i), lat, speech) for i in range(conc)))
+            await asyncio.gather(*(client_loop(asr, i, per_client, np.random.default_rng(777 + rank * 1000 + i), lat, speech)
+                                   for i in range(conc)))
 
         l0, e0 = asr.batcher.launches, asr.batcher.encoded
         t0 = time.perf_counter()
         asyncio.run(run())
         wall = time.perf_counter() - t0
-        ls = np.sort(np.array(lat)) * 1e3
-        out[conc] = {"utterances": len(lat), "utterances_per_s": len(lat) / wall, "speech_s_per_s": float(np.sum(speech)) / wall,
-                     "audio_s_per_s_30s_windows": 30.0 * len(lat) / wall, "mean_batch": (asr.batcher.encoded - e0) / max(1, asr.batcher.launches - l0),
-                     "latency_ms": {"p50": float(ls[len(ls) // 2]), "p90": float(ls[int(0.9 * len(ls))]), "p99": float(ls[min(len(ls) - 1, int(0.99 * len(ls)))]), "max": float(ls[-1])}}
-        print(conc, json.dumps(out[conc]), flush=True)
-    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump({"mode": "eager" if args.eager else "cuda-graph buckets", "workload": args.workload, "levels": out},
-              open(os.path.join(ROOT, "gpurun_out", "streaming_sim" + ("_eager" if args.eager else "") + ".json"), "w"), indent=1)
+        parts = gather_host({"lat": lat, "speech": float(np.sum(speech)), "wall": wall, "clients": conc,
+                             "mean_batch": (asr.batcher.encoded - e0) / max(1, asr.batcher.launches - l0)})
+        if rank != 0:
+            continue
+        parts = [p for p in parts if p]
+        lat_all = [x for p in parts for x in p["lat"]]
+        wall = max(p["wall"] for p in parts)
+        ls = np.sort(np.array(lat_all)) * 1e3
+        out[total_conc] = {"utterances": len(lat_all), "servers": len(parts), "utterances_per_s": len(lat_all) / wall,
+                           "speech_s_per_s": sum(p["speech"] for p in parts) / wall,
+                           "audio_s_per_s_30s_windows": 30.0 * len(lat_all) / wall,
+                           "mean_batch": float(np.mean([p["mean_batch"] for p in parts])),
+                           "latency_ms": {"p50": float(ls[len(ls) // 2]), "p90": float(ls[int(0.9 * len(ls))]),
+                                          "p99": float(ls[min(len(ls) - 1, int(0.99 * len(ls)))]), "max": float(ls[-1])}}
+        print(total_conc, json.dumps(out[total_conc]), flush=True)
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        name = "streaming_sim" + ("_eager" if args.eager else "") + (f"_{world}gpu" if world > 1 else "") + ".json"
+        json.dump({"mode": "eager" if args.eager else "cuda-graph buckets", "workload": args.workload, "n_gpus": world,
+                   "levels": out}, open(os.path.join(ROOT, "gpurun_out", name), "w"), indent=1)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
