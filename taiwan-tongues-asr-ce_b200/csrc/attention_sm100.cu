@@ -240,10 +240,12 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     tmem_alloc<1>(smem_u32(&s.tmem_ptr), 512);
     tmem_relinquish<1>();
   }
+  pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *reinterpret_cast<volatile uint32_t*>(&s.tmem_ptr), 0);
+  pdl_wait();   // the QKV GEMM's output is visible from here on (ptx_sm100.cuh: programmatic dependent launch)
 
   auto item_coords = [&](int item, int& b, int& h, int& q0) {
     const int qb = item % p.q_blocks;
@@ -623,8 +625,15 @@ cudaError_t attention_launch(const void* qkv, void* out, int batch, int n_ctx, i
     if (e != cudaSuccess) return e;
   }
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  attention_kernel<<<grid, kAttnThreads, smem, stream>>>(p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kAttnThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_launch_attr(&attr[0]);
+  return cudaLaunchKernelEx(&cfg, attention_kernel, p);
 }
 
 }  // namespace ttasr

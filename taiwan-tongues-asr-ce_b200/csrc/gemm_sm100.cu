@@ -51,8 +51,13 @@ struct Cfg {
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // staging ring of 16 KB slabs (each slab is in flight from its TMA prefetch / first write until its store is read).
-  // The split epilogue moves slabs in (hi, lo) PAIRS: kNPair pairs = 2 * kNPair buffers.
-  static constexpr int kNPair = (BN == 256 && CG == 1) ? 2 : 3;
+  // The split epilogue moves slabs in (hi, lo) PAIRS: kNPair pairs = 2 * kNPair buffers.  Two pairs: the same 64 KB and
+  // the same 128 columns of addend look-ahead as the fp32 variant's four 32-column slabs, and — what matters more — the
+  // same five-stage operand ring (three pairs leave only four stages: measured -20 % on fc2 and out-proj at B = 256).
+#ifndef TTASR_GEMM_SPLIT_PAIRS
+#define TTASR_GEMM_SPLIT_PAIRS 2
+#endif
+  static constexpr int kNPair = (BN == 256 && CG == 1) ? 2 : TTASR_GEMM_SPLIT_PAIRS;
   static constexpr int kNBuf = (EPI == kEpiSplit) ? 2 * kNPair : 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kStagesRaw = (kMaxSmem - 1024 - kBarBytes - kNBuf * kSlabBytes) / kStageBytes;
@@ -184,10 +189,12 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
     tmem_alloc<CG>(tmem_slot, C::kTmemCols);
     tmem_relinquish<CG>();
   }
+  pdl_trigger();   // the next kernel of the stream may start its own prologue on SMs this grid leaves
   tc_fence_before();
   if constexpr (CG == 2) cluster_sync(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; its results are visible from here on
 
   auto tile_coords = [&](int tile, int& b, int& t0, int& n0) {
     const int nt = tile % p.tiles_n;
@@ -326,19 +333,26 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
       float ln_a = 1.f, ln_b = 0.f;      // consumer side: out = ln_a * acc + ln_b * c1[n] + c2[n]
       const bool ln_in = (EPI == kEpiBf16) && (p.ln_stats_in != nullptr);
       if (ln_in) {
-        // combine the partial (mean_i, M2_i) pairs (equal counts) in a fixed order: bit-reproducible statistics
+        // combine the partial (mean_i, M2_i) pairs (equal counts) in a fixed order: bit-reproducible statistics.  All
+        // partials of the row are requested up front (<= kMaxLnParts independent 8-byte loads in flight: one L2 round
+        // trip per tile instead of one per partial) and both passes then run out of registers.
+        constexpr int kMaxLnParts = 20;   // d_model <= 1280, one partial per 64 columns
         float mean = 0.f, m2 = 0.f;
         if (row_ok) {
           const float2* st = p.ln_stats_in + grow * p.ln_parts_in;
+          float2 part[kMaxLnParts];
+#pragma unroll
+          for (int i = 0; i < kMaxLnParts; ++i) part[i] = (i < p.ln_parts_in) ? __ldg(st + i) : make_float2(0.f, 0.f);
           float msum = 0.f;
-          for (int i = 0; i < p.ln_parts_in; ++i) msum += __ldg(st + i).x;
+#pragma unroll
+          for (int i = 0; i < kMaxLnParts; ++i) msum += part[i].x;       // absent partials contribute exact zeros
           mean = msum / static_cast<float>(p.ln_parts_in);
           float dev2 = 0.f;
-          for (int i = 0; i < p.ln_parts_in; ++i) {
-            const float2 t = __ldg(st + i);
-            const float dm = t.x - mean;
-            dev2 = fmaf(dm, dm, dev2);
-            m2 += t.y;
+#pragma unroll
+          for (int i = 0; i < kMaxLnParts; ++i) {
+            const float dm = part[i].x - mean;
+            if (i < p.ln_parts_in) dev2 = fmaf(dm, dm, dev2);
+            m2 += part[i].y;
           }
           m2 = fmaf(p.ln_part_n, dev2, m2);
         }
@@ -568,13 +582,13 @@ cudaError_t launch_variant(const GemmParams& p, int num_sms, cudaStream_t stream
   cfg.blockDim = dim3(kThreadsGemm);
   cfg.dynamicSmemBytes = C::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 1 + pdl_launch_attr(&attr[1]);
   return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
@@ -717,8 +731,9 @@ cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, con
     if (c.ln_parts_out) *c.ln_parts_out = c.n / 64;
   }
   if (c.ln_stats_in) {
-    if (c.out_f32 || c.split || !c.ln_c1 || c.ln_parts_in <= 0 || c.mode != kGemmPlain || c.a_inner % c.ln_parts_in != 0) {
-      *why = "gemm: LayerNorm-folded input needs bf16 output, ln_c1 and ln_parts_in dividing K";
+    if (c.out_f32 || c.split || !c.ln_c1 || c.ln_parts_in <= 0 || c.ln_parts_in > 20 || c.mode != kGemmPlain ||
+        c.a_inner % c.ln_parts_in != 0) {
+      *why = "gemm: LayerNorm-folded input needs bf16 output, ln_c1 and 1..20 ln_parts_in dividing K";
       return cudaErrorInvalidValue;
     }
     p.ln_stats_in = static_cast<const float2*>(c.ln_stats_in);

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
                                                         void* __restrict__ y, long long rows, int d) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  pdl_trigger();
+  pdl_wait();
   if (row >= rows) return;
   const int nvec = d >> 7;  // float4 per lane
   float4 v[kMaxVec];
@@ -81,6 +83,19 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const void* __restrict__
   }
 }
 
+template <bool OUT_F32, bool SPLIT_IN>
+cudaError_t launch_ln(unsigned grid, cudaStream_t stream, const void* x, const void* x_lo, const float* g, const float* b,
+                      void* y, long long rows, int d) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_launch_attr(&attr[0]);
+  return cudaLaunchKernelEx(&cfg, layernorm_kernel<OUT_F32, SPLIT_IN>, x, x_lo, g, b, y, rows, d);
+}
+
 }  // namespace
 
 cudaError_t layernorm_launch(const float* x, const float* g, const float* b, void* y, long long rows, int d,
@@ -88,11 +103,8 @@ cudaError_t layernorm_launch(const float* x, const float* g, const float* b, voi
   if (d % 128 != 0 || d <= 0 || d > 128 * kMaxVec) return cudaErrorInvalidValue;
   if (rows <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  if (out_f32)
-    layernorm_kernel<true, false><<<grid, 256, 0, stream>>>(x, nullptr, g, b, y, rows, d);
-  else
-    layernorm_kernel<false, false><<<grid, 256, 0, stream>>>(x, nullptr, g, b, y, rows, d);
-  return cudaGetLastError();
+  return out_f32 ? launch_ln<true, false>(grid, stream, x, nullptr, g, b, y, rows, d)
+                 : launch_ln<false, false>(grid, stream, x, nullptr, g, b, y, rows, d);
 }
 
 cudaError_t layernorm_split_launch(const void* x_hi, const void* x_lo, const float* g, const float* b, void* y,
@@ -100,11 +112,8 @@ cudaError_t layernorm_split_launch(const void* x_hi, const void* x_lo, const flo
   if (d % 128 != 0 || d <= 0 || d > 128 * kMaxVec) return cudaErrorInvalidValue;
   if (rows <= 0) return cudaSuccess;
   const unsigned grid = static_cast<unsigned>((rows + 7) / 8);
-  if (out_f32)
-    layernorm_kernel<true, true><<<grid, 256, 0, stream>>>(x_hi, x_lo, g, b, y, rows, d);
-  else
-    layernorm_kernel<false, true><<<grid, 256, 0, stream>>>(x_hi, x_lo, g, b, y, rows, d);
-  return cudaGetLastError();
+  return out_f32 ? launch_ln<true, true>(grid, stream, x_hi, x_lo, g, b, y, rows, d)
+                 : launch_ln<false, true>(grid, stream, x_hi, x_lo, g, b, y, rows, d);
 }
 
 }  // namespace ttasr

@@ -58,6 +58,21 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
   return r;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// The encoder's kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel may START (carve
+// shared memory, init barriers, allocate TMEM, prefetch descriptors) while its predecessor in the stream drains, and
+// must call pdl_wait() before it touches global memory the predecessor wrote (or writes memory it may still read).
+// pdl_trigger() tells the scheduler this grid no longer minds its successor starting.  Small batches (streaming) are
+// bounded by exactly these per-kernel ramps; at large batch it changes nothing.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// host side: fills `attr` with the PDL launch attribute; returns the number of attributes written
+inline int pdl_launch_attr(cudaLaunchAttribute* attr) {
+  attr->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr->val.programmaticStreamSerializationAllowed = 1;
+  return 1;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
