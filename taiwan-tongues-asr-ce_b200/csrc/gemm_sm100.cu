@@ -51,14 +51,11 @@ struct Cfg {
   static constexpr int kBBytes = kBRows * kBK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   // staging ring of 16 KB slabs (each slab is in flight from its TMA prefetch / first write until its store is read).
-  // The split epilogue moves slabs in (hi, lo) PAIRS: kNPair pairs = 2 * kNPair buffers.  Two pairs: the same 64 KB and
-  // the same 128 columns of addend look-ahead as the fp32 variant's four 32-column slabs, and — what matters more — the
-  // same five-stage operand ring (three pairs leave only four stages: measured -20 % on fc2 and out-proj at B = 256).
-#ifndef TTASR_GEMM_SPLIT_PAIRS
-#define TTASR_GEMM_SPLIT_PAIRS 2
-#endif
-  static constexpr int kNPair = (BN == 256 && CG == 1) ? 2 : TTASR_GEMM_SPLIT_PAIRS;
-  static constexpr int kNBuf = (EPI == kEpiSplit) ? 2 * kNPair : 4;
+  // The split epilogue works on 32-column slabs like the fp32 one: a ring entry holds the (hi, lo) PAIR of a slab
+  // (2 x 128 rows x 64 B), so four entries give the same 64 KB, the same addend look-ahead (two slabs in work, two in
+  // flight) and the same five-stage operand ring as the fp32 variant.  (Measured at B = 256: 64-column pairs with three
+  // entries leave four operand stages, -20 % on fc2 / out-proj; with two entries nothing is prefetched, -45 % on out-proj.)
+  static constexpr int kNBuf = 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kStagesRaw = (kMaxSmem - 1024 - kBarBytes - kNBuf * kSlabBytes) / kStageBytes;
   static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
@@ -129,10 +126,12 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
   constexpr bool SPLIT = (EPI == kEpiSplit);
   constexpr int kStages = C::kStages;
   constexpr int kNBuf = C::kNBuf;
-  constexpr int kRing = SPLIT ? C::kNPair : kNBuf;   // entries of the staging ring (slabs, or slab pairs)
-  constexpr int kSlabCols = OUT_F32 ? 32 : 64;
+  constexpr int kRing = kNBuf;                        // entries of the staging ring (slabs, or (hi, lo) slab pairs)
+  constexpr int kSlabCols = (OUT_F32 || SPLIT) ? 32 : 64;
+  constexpr uint32_t kHalfSlab = kSlabBytes / 2;      // split: 128 rows x 64 B (hi at +0, lo at +kHalfSlab)
   constexpr int kNSlab = BN / kSlabCols;
   static_assert(kNSlab % 2 == 0, "two epilogue warpgroups take alternate slabs");
+  static_assert(!SPLIT || kNSlab % 4 == 0, "split epilogue: each warpgroup takes PAIRS of adjacent slabs (64 columns)");
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = smem_u32(smem_raw);
@@ -151,7 +150,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
   const uint32_t tmem_slot = sBar + 8u * (2 * kStages + 4 + 3 * kNBuf);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem0));
   // staging address of ring entry e (split: the hi slab; the lo slab follows it)
-  auto slab_addr = [&](uint32_t e) { return sE + e * (SPLIT ? 2u : 1u) * kSlabBytes; };
+  auto slab_addr = [&](uint32_t e) { return sE + e * kSlabBytes; };
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
           const uint32_t e = q % kRing;
           mbar_wait(out_ready(e), (q / kRing) & 1);
           tma_store_3d(&p.tm_out, slab_addr(e), n0 + s * kSlabCols, t0, b);
-          if (SPLIT && p.has_lo) tma_store_3d(&p.tm_out2, slab_addr(e) + kSlabBytes, n0 + s * kSlabCols, t0, b);
+          if (SPLIT && p.has_lo) tma_store_3d(&p.tm_out2, slab_addr(e) + kHalfSlab, n0 + s * kSlabCols, t0, b);
           tma_store_commit();
           if (q > 0) {  // the previous store has finished reading its slab(s): recycle them
             tma_store_wait_read<1>();
@@ -300,9 +299,9 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
           const uint32_t e = q % kRing;
           mbar_wait(buf_free(e), ((q / kRing) & 1) ^ 1);
           if constexpr (SPLIT) {
-            mbar_arrive_expect_tx(add_full(e), p.has_lo ? 2 * kSlabBytes : kSlabBytes);
+            mbar_arrive_expect_tx(add_full(e), p.has_lo ? 2 * kHalfSlab : kHalfSlab);
             tma_load_3d(slab_addr(e), &p.tm_add, add_full(e), n0 + s * kSlabCols, t0, add_b);
-            if (p.has_lo) tma_load_3d(slab_addr(e) + kSlabBytes, &p.tm_add2, add_full(e), n0 + s * kSlabCols, t0, add_b);
+            if (p.has_lo) tma_load_3d(slab_addr(e) + kHalfSlab, &p.tm_add2, add_full(e), n0 + s * kSlabCols, t0, add_b);
           } else {
             mbar_arrive_expect_tx(add_full(e), kSlabBytes);
             tma_load_3d(slab_addr(e), &p.tm_add, add_full(e), n0 + s * kSlabCols, t0, add_b);
@@ -360,18 +359,102 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
         ln_a = rsqrtf(var + p.ln_eps);
         ln_b = -ln_a * mean;
       }
+      // producer side (split epilogue): sums of (v - K) and (v - K)^2 over this row's 64 hi values of a slab pair, K = the
+      // first of them (a shift inside the data's own range keeps the one-pass variance well conditioned).  One partial
+      // per 64 columns whatever the tile shape, so the statistics do not depend on the launcher's choice of BN / CG.
+      float st_k = 0.f;
+      f32x2_t st_s1 = pack2(0.f, 0.f), st_s2 = pack2(0.f, 0.f);
 #pragma unroll 1
-      for (int s = wg; s < kNSlab; s += 2) {
+      for (int i = 0; i < kNSlab / 2; ++i) {
+        // slab order of this warpgroup: alternate slabs, or (split) alternate PAIRS of adjacent slabs
+        const int s = SPLIT ? ((i >> 1) * 4 + 2 * wg + (i & 1)) : (2 * i + wg);
         const uint32_t q = q0 + s;
         const uint32_t e = q % kRing;
         const uint32_t use = (q / kRing) & 1;
         const uint32_t slab = slab_addr(e);
-        const bool last = (s + 2 >= kNSlab);
-        // producer side (split epilogue): sums of (v - K) and (v - K)^2 over this row's 64 hi values of the slab, K = the
-        // first of them (a shift inside the data's own range keeps the one-pass variance well conditioned).  One partial
-        // per 64 columns whatever the tile shape, so the statistics do not depend on the launcher's choice of BN / CG.
-        float st_k = 0.f;
-        f32x2_t st_s1 = pack2(0.f, 0.f), st_s2 = pack2(0.f, 0.f);
+        const bool last = (i + 1 == kNSlab / 2);
+
+        if constexpr (SPLIT) {
+          // x' = act(acc + bias) + (add_hi + add_lo) in fp32; out_hi = bf16(x'), out_lo = bf16(x' - out_hi)
+          uint32_t acc[32];
+          tmem_ld_32x32(acc_addr + s * 32, acc);
+          tmem_wait_ld();
+          if (last) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
+          }
+          mbar_wait(add_full(e), use);                      // addend (hi, lo) slabs landed (prefetched by warp 3)
+          const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 32);
+          const uint32_t srow = slab + row * 64;            // 64-byte rows, CU_TENSOR_MAP_SWIZZLE_64B
+          const uint32_t sw = (row >> 1) & 3;
+          if ((i & 1) == 0) {
+            st_s1 = pack2(0.f, 0.f);
+            st_s2 = pack2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {                     // 16-byte chunk = 8 bf16 columns
+            const float4 b0 = __ldg(bias4 + 2 * c), b1 = __ldg(bias4 + 2 * c + 1);
+            const uint32_t addr = srow + ((c ^ sw) << 4);
+            f32x2_t x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const f32x2_t bb = (j == 0) ? pack2(b0.x, b0.y) : (j == 1) ? pack2(b0.z, b0.w) : (j == 2) ? pack2(b1.x, b1.y) : pack2(b1.z, b1.w);
+              x[j] = add2(pack2(__uint_as_float(acc[8 * c + 2 * j]), __uint_as_float(acc[8 * c + 2 * j + 1])), bb);
+              if constexpr (ACT == 1) x[j] = gelu_erf_f32x2(x[j]);
+            }
+            uint32_t h[4];
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(addr));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float f0, f1;
+              bf16x2_to_f32(h[j], f0, f1);
+              x[j] = add2(x[j], pack2(f0, f1));
+            }
+            if (p.has_lo) {
+              uint32_t l[4];
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(addr + kHalfSlab));
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float f0, f1;
+                bf16x2_to_f32(l[j], f0, f1);
+                x[j] = add2(x[j], pack2(f0, f1));
+              }
+            }
+            uint32_t oh[4], ol[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x0, x1, f0, f1;
+              unpack2(x[j], x0, x1);
+              oh[j] = pack_bf16x2(x0, x1);
+              bf16x2_to_f32(oh[j], f0, f1);
+              if ((i & 1) == 0 && c == 0 && j == 0) st_k = f0;
+              const f32x2_t hv = pack2(f0, f1);
+              const f32x2_t dv = add2(hv, pack2(-st_k, -st_k));
+              st_s1 = add2(st_s1, dv);
+              st_s2 = fma2(dv, dv, st_s2);
+              float r0, r1;
+              unpack2(add2(x[j], pack2(-f0, -f1)), r0, r1);
+              ol[j] = pack_bf16x2(r0, r1);
+            }
+            sts128u(addr, oh[0], oh[1], oh[2], oh[3]);
+            if (p.has_lo) sts128u(addr + kHalfSlab, ol[0], ol[1], ol[2], ol[3]);
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
+          __syncwarp();
+          if (lane == 0) mbar_arrive(out_ready(e));
+          if ((i & 1) == 1 && p.ln_stats_out != nullptr && row_ok) {
+            // mean = K + s1 / 64, M2 = s2 - s1^2 / 64 over the 64 columns of this slab pair
+            float a0, a1, e0, e1;
+            unpack2(st_s1, a0, a1);
+            unpack2(st_s2, e0, e1);
+            const float s1 = a0 + a1, s2 = e0 + e1;
+            const float mean = fmaf(s1, 1.0f / 64.0f, st_k);
+            const float m2 = fmaxf(fmaf(-s1, s1 * (1.0f / 64.0f), s2), 0.f);
+            p.ln_stats_out[grow * (p.n >> 6) + ((n0 + s * 32) >> 6)] = make_float2(mean, m2);
+          }
+          continue;
+        }
 
         if constexpr (OUT_F32) {
           uint32_t acc[32];
@@ -424,8 +507,7 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(mapa(tempty_bar(as), 0));
           }
-          if (SPLIT) mbar_wait(add_full(e), use);           // addend (hi, lo) slabs landed (prefetched by warp 3)
-          else mbar_wait(buf_free(e), use ^ 1);
+          mbar_wait(buf_free(e), use ^ 1);
           const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + s * 64);
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 16-byte chunk = 8 bf16 columns
@@ -434,54 +516,6 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
             uint32_t aa[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) aa[i] = a[i];
-            if constexpr (SPLIT) {
-              // x' = act(acc + bias) + (add_hi + add_lo) in fp32; out_hi = bf16(x'), out_lo = bf16(x' - out_hi)
-              const uint32_t addr = slab + row_off + ((c ^ swz) << 4);
-              f32x2_t x[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const f32x2_t bb = (j == 0) ? pack2(b0.x, b0.y) : (j == 1) ? pack2(b0.z, b0.w) : (j == 2) ? pack2(b1.x, b1.y) : pack2(b1.z, b1.w);
-                x[j] = add2(pack2(__uint_as_float(aa[2 * j]), __uint_as_float(aa[2 * j + 1])), bb);
-                if constexpr (ACT == 1) x[j] = gelu_erf_f32x2(x[j]);
-              }
-              uint32_t h[4];
-              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(h[0]), "=r"(h[1]), "=r"(h[2]), "=r"(h[3]) : "r"(addr));
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float f0, f1;
-                bf16x2_to_f32(h[j], f0, f1);
-                x[j] = add2(x[j], pack2(f0, f1));
-              }
-              if (p.has_lo) {
-                uint32_t l[4];
-                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(l[0]), "=r"(l[1]), "=r"(l[2]), "=r"(l[3]) : "r"(addr + kSlabBytes));
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  float f0, f1;
-                  bf16x2_to_f32(l[j], f0, f1);
-                  x[j] = add2(x[j], pack2(f0, f1));
-                }
-              }
-              uint32_t oh[4], ol[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float x0, x1, f0, f1;
-                unpack2(x[j], x0, x1);
-                oh[j] = pack_bf16x2(x0, x1);
-                bf16x2_to_f32(oh[j], f0, f1);
-                if (c == 0 && j == 0) st_k = f0;
-                const f32x2_t hv = pack2(f0, f1);
-                const f32x2_t dv = add2(hv, pack2(-st_k, -st_k));
-                st_s1 = add2(st_s1, dv);
-                st_s2 = fma2(dv, dv, st_s2);
-                float r0, r1;
-                unpack2(add2(x[j], pack2(-f0, -f1)), r0, r1);
-                ol[j] = pack_bf16x2(r0, r1);
-              }
-              sts128u(addr, oh[0], oh[1], oh[2], oh[3]);
-              if (p.has_lo) sts128u(addr + kSlabBytes, ol[0], ol[1], ol[2], ol[3]);
-              continue;
-            }
             if (ln_in) {  // LayerNorm folded in: x = ln_a * acc + (ln_b * c1 + c2); the code below then adds "bias" 0
               const float4* c14 = reinterpret_cast<const float4*>(p.ln_c1 + n0 + s * 64);
               const float4 k0 = __ldg(c14 + 2 * c), k1 = __ldg(c14 + 2 * c + 1);
@@ -529,16 +563,6 @@ __global__ void __launch_bounds__(kThreadsGemm, 1) gemm_kernel(const __grid_cons
         fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA store
         __syncwarp();
         if (lane == 0) mbar_arrive(out_ready(e));
-        if (SPLIT && p.ln_stats_out != nullptr && row_ok) {
-          // mean = K + s1 / 64, M2 = s2 - s1^2 / 64
-          float a0, a1, e0, e1;
-          unpack2(st_s1, a0, a1);
-          unpack2(st_s2, e0, e1);
-          const float s1 = a0 + a1, s2 = e0 + e1;
-          const float mean = fmaf(s1, 1.0f / 64.0f, st_k);
-          const float m2 = fmaxf(fmaf(-s1, s1 * (1.0f / 64.0f), s2), 0.f);
-          p.ln_stats_out[grow * (p.n >> 6) + ((n0 >> 6) + s)] = make_float2(mean, m2);
-        }
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
@@ -784,15 +808,17 @@ cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, con
     if (r != CUDA_SUCCESS) { *why = "gemm: cuTensorMapEncodeTiled(addend) failed"; return cudaErrorInvalidValue; }
   }
   if (c.split) {
-    uint32_t box[3] = {64u, static_cast<uint32_t>(kBM), 1};
+    uint32_t box[3] = {32u, static_cast<uint32_t>(kBM), 1};
     uint64_t odims[3] = {static_cast<uint64_t>(c.n), static_cast<uint64_t>(c.rows), static_cast<uint64_t>(c.nbatch)};
     uint64_t ostr[2] = {odims[0] * 2, odims[0] * odims[1] * 2};
     uint64_t adims[3] = {odims[0], odims[1], static_cast<uint64_t>(c.addend_bcast ? 1 : c.nbatch)};
-    r = encode_tmap(&p.tm_add, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.addend_hi, adims, ostr, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    r = encode_tmap(&p.tm_add, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.addend_hi, adims, ostr, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (r == CUDA_SUCCESS && c.addend_lo)
-      r = encode_tmap(&p.tm_add2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.addend_lo, adims, ostr, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      r = encode_tmap(&p.tm_add2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.addend_lo, adims, ostr, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    if (r == CUDA_SUCCESS)   // hi output: 32-column boxes like the addend (replaces the generic 64-column map made above)
+      r = encode_tmap(&p.tm_out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.out, odims, ostr, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (r == CUDA_SUCCESS && c.out_lo)
-      r = encode_tmap(&p.tm_out2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.out_lo, odims, ostr, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      r = encode_tmap(&p.tm_out2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, c.out_lo, odims, ostr, box, CU_TENSOR_MAP_SWIZZLE_64B);
     if (r != CUDA_SUCCESS) { *why = "gemm: cuTensorMapEncodeTiled(split operands) failed"; return cudaErrorInvalidValue; }
   }
 

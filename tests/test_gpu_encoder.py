@@ -1,5 +1,10 @@
 """Encoder parity through the drop-in Python surface -> C ABI -> sm_100a kernels, against the fp32 oracle on the same
-bf16-rounded weights.  Stated tolerance: max-abs <= 0.10, mean-abs <= 0.01, cosine >= 0.9999."""
+bf16-rounded weights.
+
+Gates, frozen in round 2 at about twice the error measured on the B200 for the default (split residual stream) path with
+bf16 output (profiles/r2_parity_report.json; max-abs, a single-element statistic, gets 2.5x): per architecture, since the
+error grows with depth.  For scale, Hugging Face's own encoder run in bf16 on the same GPU (the control run SURVEY 8d asks
+for) sits at 0.146 / 0.0109 / 0.99990 for large-v3 — five times further from the fp32 oracle than this library."""
 import os
 
 import numpy as np
@@ -9,7 +14,14 @@ from oracle import encoder as OE
 from oracle import frontend as OF
 
 pytestmark = pytest.mark.gpu
-MAX_ABS, MEAN_ABS, COS = 0.10, 0.01, 0.9999
+GATES = {  # measured (split, bf16 out): micro ~tiny; tiny 0.013 / 0.0017 / 0.9999975; small 0.022 / 0.0030 / 0.9999930;
+    #           large-v3 0.029 / 0.0040 / 0.9999875
+    "micro": (0.035, 0.0035, 0.999995), "tiny": (0.035, 0.0035, 0.999995), "small": (0.055, 0.006, 0.999985),
+    "large-v3": (0.07, 0.008, 0.999975),
+    # synthetic stress streams (massive-activation channels, token-mean offset): the round-1 provisional gate
+    "stress": (0.10, 0.01, 0.9999),
+}
+MAX_ABS, MEAN_ABS, COS = GATES["large-v3"]   # the loosest: for checks that do not name their architecture
 
 
 def _cfg(arch):
@@ -25,9 +37,10 @@ def _build(arch_name, seed=0):
     return arch, w, B200WhisperEncoder(_cfg(arch), w)
 
 
-def _check(got, ref):
+def _check(got, ref, arch="large-v3"):
     s = OE.parity_stats(got, ref)
-    assert s["max_abs"] <= MAX_ABS and s["mean_abs"] <= MEAN_ABS and s["cosine"] >= COS, s
+    max_abs, mean_abs, cos = GATES[arch]
+    assert s["max_abs"] <= max_abs and s["mean_abs"] <= mean_abs and s["cosine"] >= cos, (arch, s)
     return s
 
 
@@ -41,10 +54,10 @@ def test_encoder_matches_fp32_oracle(cuda_device, arch_name):
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
     got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
     assert got.shape == (3, 1500, arch.d_model)
-    _check(got, ref)
+    _check(got, ref, arch_name)
     got16 = enc.encode(feats)
     assert got16.dtype == torch.bfloat16
-    _check(got16.float().cpu().numpy(), ref)
+    _check(got16.float().cpu().numpy(), ref, arch_name)
     # same chunk, other batch position -> identical bits (SURVEY.md section 8e determinism)
     again = enc.encode(feats[[2, 0]], out_dtype=torch.float32).cpu().numpy()
     assert np.array_equal(again[1], got[0]) and np.array_equal(again[0], got[2])
@@ -57,7 +70,7 @@ def test_golden_fixture_tiny(cuda_device):
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "encoder_hf.npz"))
     feats = OF.log_mel(OF.synth_noise(), arch.n_mels)[None]
     got = enc.encode(feats, out_dtype=torch.float32)[0].cpu().numpy()
-    _check(got[::25], g["enc_tiny_sub"])
+    _check(got[::25], g["enc_tiny_sub"], "tiny")
 
 
 def test_forward_is_a_drop_in_for_hf_encoder(cuda_device):
@@ -82,12 +95,12 @@ def test_pcm_to_hidden_pipeline(cuda_device):
     got = pipe.encode_device(torch.from_numpy(clips).to(cuda_device), out_dtype=torch.float32).cpu().numpy()
     feats = np.stack([OF.log_mel(c, arch.n_mels) for c in clips])
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
-    _check(got, ref)
+    _check(got, ref, "tiny")
     host = torch.from_numpy(clips).pin_memory()
     out_host = torch.empty((2, 1500, arch.d_model), dtype=torch.bfloat16).pin_memory()
     pipe.encode_host(host, out_host)
     torch.cuda.synchronize()
-    _check(out_host.float().numpy(), ref)
+    _check(out_host.float().numpy(), ref, "tiny")
 
 
 @pytest.mark.parametrize("arch_name", ["small"])
@@ -99,7 +112,7 @@ def test_encoder_small_config2_sample(cuda_device, arch_name):
     feats = np.stack([OF.log_mel(OF.synth_noise(11), arch.n_mels), OF.log_mel(OF.synth_tones(12), arch.n_mels)])
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
     got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
-    _check(got, ref)
+    _check(got, ref, arch_name)
 
 
 def test_pipelined_host_stream_matches_single_calls(cuda_device):
@@ -154,7 +167,7 @@ def test_streaming_plugin_end_to_end(cuda_device, use_graphs):
     for p in pcm:
         feats = OF.log_mel(p.astype(np.float32) / 32768.0, arch.n_mels)[None]
         ref = OE.encoder_forward(torch.from_numpy(feats), w, arch)
-        _check(seen[len(p)].numpy(), ref.numpy())
+        _check(seen[len(p)].numpy(), ref.numpy(), "micro")
 
 
 def test_faster_whisper_seams(cuda_device):
@@ -177,7 +190,7 @@ def test_faster_whisper_seams(cuda_device):
     hidden = model.encode(window)
     padded_window = np.concatenate([window, np.zeros((arch.n_mels, 3000 - window.shape[1]), np.float32)], axis=1)
     ref_h = OE.encoder_forward(torch.from_numpy(padded_window[None]), w, arch)
-    _check(hidden.float().cpu().numpy(), ref_h.numpy())
+    _check(hidden.float().cpu().numpy(), ref_h.numpy(), "micro")
 
 
 def test_large_v3_single_chunk_against_oracle(cuda_device):
@@ -189,7 +202,7 @@ def test_large_v3_single_chunk_against_oracle(cuda_device):
     feats = OF.log_mel(OF.synth_tones(31), arch.n_mels)[None]
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
     got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
-    s = _check(got, ref)
+    s = _check(got, ref, "large-v3")
     print("large-v3 parity:", s)
 
 
@@ -323,7 +336,7 @@ def test_residual_modes_match_oracle_and_each_other(cuda_device, arch_name):
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
     out = {m: e.encode(feats, out_dtype=torch.float32) for m, e in enc.items()}
     for m in ("split", "f32"):
-        print(arch_name, m, _check(out[m].cpu().numpy(), ref))
+        print(arch_name, m, _check(out[m].cpu().numpy(), ref, arch_name))
     print(arch_name, "bf16", OE.parity_stats(out["bf16"].cpu(), ref))
     s = OE.parity_stats(out["split"].cpu(), out["f32"].cpu())
     assert s["max_abs"] <= 0.05 and s["cosine"] >= 0.99995, s
@@ -360,7 +373,7 @@ def test_residual_stream_with_outlier_channels_and_offset(cuda_device, residual)
     feats = np.stack([OF.log_mel(OF.synth_noise(41), arch.n_mels), OF.log_mel(OF.synth_tones(42), arch.n_mels)])
     ref = OE.encoder_forward(torch.from_numpy(feats), w, arch).numpy()
     got = enc.encode(feats, out_dtype=torch.float32).cpu().numpy()
-    s = _check(got, ref)
+    s = _check(got, ref, "stress")
     print(f"outlier/offset stream, residual={residual}: {s}")
 
 
@@ -420,7 +433,7 @@ def test_plugin_is_constructible_from_the_factory_kwargs(cuda_device, tmp_path):
         torch.from_numpy(np.stack([long_pcm[:480000], np.pad(long_pcm[480000:], (0, 480000 - (len(long_pcm) - 480000)))])
                          ).to(cuda_device),
         n_valid=torch.tensor([480000, len(long_pcm) - 480000], dtype=torch.int32, device=cuda_device))
-    _check(hidden.float().cpu().numpy(), ref.numpy())
+    _check(hidden.float().cpu().numpy(), ref.numpy(), "micro")
     # without a decoder and without a Hugging Face directory there is nothing to decode with: say so at construction
     with pytest.raises(Exception):
         B200ASR(model_size="my-whisper-ct2", model_root=str(tmp_path))

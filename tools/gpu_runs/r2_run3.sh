@@ -3,7 +3,7 @@
 set -x
 mkdir -p gpurun_out
 O=gpurun_out
-timeout 400 python -m pytest tests/test_gpu_ops.py tests/test_gpu_encoder.py -m gpu -q --timeout=240 -x 2>&1 | tail -30 > $O/r2c_pytest.log
+timeout 400 python -m pytest tests/test_gpu_ops.py tests/test_gpu_encoder.py tests/test_gpu_bench_parity.py -m gpu -q -s --timeout=300 -x 2>&1 | grep -v "^$" | tail -60 > $O/r2c_pytest.log
 for mode in split f32; do
   timeout 240 python bench.py --steps 6 --warmup 3 --residual $mode --no-cpu-baseline --no-library-baseline > $O/r2c_bench_$mode.json 2> $O/r2c_bench_$mode.err
 done
