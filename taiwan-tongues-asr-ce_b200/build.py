@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libttasr_b200.so")
-SOURCES = ["frontend_logmel.cu", "ingest_resample.cu", "gemm_sm100.cu", "attention_sm100.cu", "layernorm.cu", "ttasr_abi.cu"]
+SOURCES = ["frontend_logmel.cu", "ingest_resample.cu", "gemm_sm100.cu", "attention_sm100.cu", "attention4_sm100.cu", "layernorm.cu", "ttasr_abi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

@@ -17,6 +17,10 @@
 //                              O / l -> bf16 -> smem -> TMA store.
 // The 1500 x 1500 score matrix never leaves the SM; keys beyond n_ctx in the last tile are masked to -inf.
 #include "attention_sm100.h"
+
+#include <stdlib.h>
+#include <string.h>
+
 #include "gemm_sm100.h"  // encode_tmap
 #include "ptx_sm100.cuh"
 
@@ -583,6 +587,21 @@ extern "C" __attribute__((visibility("default"))) int ttasr_debug_attention_trac
 }
 #endif
 
+// TTASR_ATTN_KERNEL selects the kernel: "2wg" (this file: two softmax warpgroups, 128-key tiles, exp sweeps in
+// anti-phase) or "4wg" (attention4_sm100.cu: four softmax warpgroups alternating 64-key steps).
+#ifndef TTASR_ATTN_DEFAULT_VARIANT
+#define TTASR_ATTN_DEFAULT_VARIANT 2
+#endif
+int attention_variant() {
+  static int v = [] {
+    const char* e = getenv("TTASR_ATTN_KERNEL");
+    if (e && !strcmp(e, "4wg")) return 4;
+    if (e && !strcmp(e, "2wg")) return 2;
+    return TTASR_ATTN_DEFAULT_VARIANT;
+  }();
+  return v;
+}
+
 cudaError_t attention_launch(const void* qkv, void* out, int batch, int n_ctx, int n_heads, int num_sms,
                              cudaStream_t stream, const char** why) {
   static const char* dummy;
@@ -590,6 +609,7 @@ cudaError_t attention_launch(const void* qkv, void* out, int batch, int n_ctx, i
   *why = nullptr;
   if (!qkv || !out) { *why = "attention: null operand"; return cudaErrorInvalidValue; }
   if (batch <= 0 || n_ctx <= 0 || n_heads <= 0) { *why = "attention: empty problem"; return cudaErrorInvalidValue; }
+  if (attention_variant() == 4) return attention4_launch(qkv, out, batch, n_ctx, n_heads, num_sms, stream, why);
   const int d = n_heads * kHeadDim;
   AttnParams p{};
   p.n_ctx = n_ctx;

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Build A/B variants of the library that differ only in the attention kernel's compile-time switches
-(csrc/attention_sm100.cu: TTASR_ATTN_*), for tools/attn_ab.py.  Only attention_sm100.cu is recompiled per variant; the
+(csrc/attention_sm100.cu, attention4_sm100.cu: TTASR_ATTN*), for tools/attn_ab.py.  Only those two are recompiled per variant; the
 other objects are taken from the default build.   python tools/build_attn_variants.py  ->  lib/variants/attn_<name>.so"""
 import os
 import subprocess
@@ -11,19 +11,14 @@ PKG = os.path.join(ROOT, "taiwan-tongues-asr-ce_b200")
 sys.path.insert(0, PKG)
 import build as B  # noqa: E402
 
-N = "TTASR_ATTN_SETMAXNREG=1"
+V4 = "TTASR_ATTN_DEFAULT_VARIANT=4"
 VARIANTS = {
-    "base": [],
-    "nreg": [N],
-    "q0p8": [N, "TTASR_ATTN_POLY_Q0=8"],
-    "all2": [N] + [f"TTASR_ATTN_POLY_Q{q}=2" for q in range(4)],
-    "all4": [N] + [f"TTASR_ATTN_POLY_Q{q}=4" for q in range(4)],
-    "q01p8_pre2": [N, "TTASR_ATTN_POLY_Q0=8", "TTASR_ATTN_POLY_Q1=8", "TTASR_ATTN_PRETOKEN=2"],
-    "q0p8_rest2": [N, "TTASR_ATTN_POLY_Q0=8"] + [f"TTASR_ATTN_POLY_Q{q}=2" for q in (1, 2, 3)],
-    "all4_pre4": [N, "TTASR_ATTN_PRETOKEN=4"] + [f"TTASR_ATTN_POLY_Q{q}=4" for q in range(4)],
-    "all2_pre4": [N, "TTASR_ATTN_PRETOKEN=4"] + [f"TTASR_ATTN_POLY_Q{q}=2" for q in range(4)],
-    "q0p8_nonreg": ["TTASR_ATTN_POLY_Q0=8"],
+    "v2": [],                                   # two softmax warpgroups, 128-key tiles (attention_sm100.cu)
+    "v4": [V4],                                 # four softmax warpgroups, 64-key steps (attention4_sm100.cu)
+    "v4p2": [V4, "TTASR_ATTN4_POLY8=2"],        # ... a quarter of the exponentials on the FMA pipe
+    "v4p4": [V4, "TTASR_ATTN4_POLY8=4"],        # ... half
 }
+ATTN_SOURCES = ["attention_sm100.cu", "attention4_sm100.cu"]
 
 
 def main():
@@ -31,18 +26,22 @@ def main():
     B.build(verbose=False)
     outdir = os.path.join(PKG, "lib", "variants")
     os.makedirs(outdir, exist_ok=True)
-    others = [os.path.join(B.OBJDIR, s.replace(".cu", ".o")) for s in B.SOURCES if s != "attention_sm100.cu"]
+    others = [os.path.join(B.OBJDIR, s.replace(".cu", ".o")) for s in B.SOURCES if s not in ATTN_SOURCES]
     for name, defs in VARIANTS.items():
         if only and name not in only:
             continue
-        obj = os.path.join(outdir, f"attn_{name}.o")
-        cmd = [B._nvcc(), *B.NVCC_FLAGS, *[f"-D{d}" for d in defs], "-I", B.CSRC, "-c",
-               os.path.join(B.CSRC, "attention_sm100.cu"), "-o", obj]
-        subprocess.run(cmd, check=True)
+        objs = []
+        for src in ATTN_SOURCES:
+            obj = os.path.join(outdir, f"attn_{name}_{src.replace('.cu', '.o')}")
+            cmd = [B._nvcc(), *B.NVCC_FLAGS, *[f"-D{d}" for d in defs], "-I", B.CSRC, "-c",
+                   os.path.join(B.CSRC, src), "-o", obj]
+            subprocess.run(cmd, check=True)
+            objs.append(obj)
         lib = os.path.join(outdir, f"attn_{name}.so")
-        subprocess.run([B._nvcc(), "-shared", "-o", lib, obj, *others, "-gencode", "arch=compute_100a,code=sm_100a",
+        subprocess.run([B._nvcc(), "-shared", "-o", lib, *objs, *others, "-gencode", "arch=compute_100a,code=sm_100a",
                         "-Xcompiler", "-fPIC", "-lpthread", "-ldl", "-lrt"], check=True)
-        os.remove(obj)
+        for obj in objs:
+            os.remove(obj)
         print("built", lib, defs)
 
 

@@ -1,5 +1,8 @@
 """Small, fixed workloads for `ncu --set full` captures of one kernel family at a time (large-v3 shapes, B chunks).
-    python tools/ncu_target.py {gemm_fc1|gemm_fc2|gemm_qkv|gemm_out|attention|frontend|layernorm|encoder} [B]"""
+    python tools/ncu_target.py {gemm_fc1|gemm_fc2|gemm_qkv|gemm_out|attention|frontend|layernorm|...} [B]
+The default encoder path (split residual stream) runs the *_ln (LayerNorm folded into the consumer) and *_split (residual
+GEMM on the (hi, lo) pair, emitting the LayerNorm partials) flavours: gemm_qkv_ln, gemm_fc1_ln, gemm_out_split,
+gemm_fc2_split, layernorm_split (the final LayerNorm)."""
 import os
 import sys
 
@@ -29,6 +32,31 @@ def main():
         for _ in range(reps):
             L.check(lib.ttasr_op_gemm(a.data_ptr(), w.data_ptr(), bias.data_ptr(), o.data_ptr() if add else None,
                                       o.data_ptr(), M, N, K, act, f32, 0, st))
+    elif what in ("gemm_qkv_ln", "gemm_fc1_ln"):
+        N, K, act = (3840, 1280, 0) if what == "gemm_qkv_ln" else (5120, 1280, 1)
+        a = torch.randn((M, K), device=dev).to(torch.bfloat16)
+        w = (torch.randn((N, K), device=dev) * K ** -0.5).to(torch.bfloat16)
+        c1, c2 = torch.randn(N, device=dev), torch.randn(N, device=dev)
+        parts = K // 64
+        stats = torch.stack([torch.zeros((M, parts), device=dev), torch.full((M, parts), 64.0, device=dev)], dim=2).contiguous()
+        o = torch.zeros((M, N), device=dev, dtype=torch.bfloat16)
+        for _ in range(reps):
+            L.check(lib.ttasr_op_gemm_lnfold(a.data_ptr(), w.data_ptr(), c1.data_ptr(), c2.data_ptr(), stats.data_ptr(), parts,
+                                             o.data_ptr(), M, N, K, act, 1e-5, 0, st))
+    elif what in ("gemm_out_split", "gemm_fc2_split"):
+        N, K = (1280, 1280) if what == "gemm_out_split" else (1280, 5120)
+        a = torch.randn((M, K), device=dev).to(torch.bfloat16)
+        w = (torch.randn((N, K), device=dev) * K ** -0.5).to(torch.bfloat16)
+        bias = torch.randn(N, device=dev)
+        xh = torch.randn((M, N), device=dev).to(torch.bfloat16)
+        xl = (torch.randn((M, N), device=dev) * 1e-3).to(torch.bfloat16)
+        stats = torch.empty((M, N // 64, 2), device=dev)
+        for _ in range(reps):
+            L.check(lib.ttasr_op_gemm_split(a.data_ptr(), w.data_ptr(), bias.data_ptr(), xh.data_ptr(), xl.data_ptr(),
+                                            xh.data_ptr(), xl.data_ptr(), stats.data_ptr(), M, N, K, 0, 0, st))
+    elif what == "layernorm_split":
+        from ttasr import B200WhisperEncoder  # noqa: F401  (the split LayerNorm has no single-op entry: run a micro encoder)
+        raise SystemExit("layernorm_split: capture it from the bench launch list (one launch per forward)")
     elif what == "attention":
         H, T = 20, 1500
         qkv = torch.randn((B, T, 3 * 64 * H), device=dev)
@@ -42,7 +70,7 @@ def main():
         fe = B200WhisperFeatureExtractor(feature_size=128)
         pcm = (0.1 * torch.randn((max(B, 64), 480000), device=dev)).clamp_(-1, 1)
         for _ in range(reps):
-            fe.extract(pcm, return_time_major=True)
+            fe.extract(pcm)          # the fp32-out variant the front-end roofline is quoted on
     elif what == "layernorm":
         x = torch.randn((M, 1280), device=dev)
         g = torch.ones(1280, device=dev)
