@@ -22,7 +22,7 @@ def main():
     st = int(torch.cuda.current_stream().cuda_stream)
     M = 1500 * B
     reps = 4
-    if what.startswith("gemm_"):
+    if what.startswith("gemm_") and not what.endswith(("_ln", "_split")):
         N, K, act, f32, add = {"gemm_fc1": (5120, 1280, 1, 0, 0), "gemm_fc2": (1280, 5120, 0, 1, 1),
                                "gemm_qkv": (3840, 1280, 0, 0, 0), "gemm_out": (1280, 1280, 0, 1, 1)}[what]
         a = torch.randn((M, K), device=dev).to(torch.bfloat16)
