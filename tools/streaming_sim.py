@@ -61,7 +61,8 @@ def main():
     pipe = ttasr.B200LogMelEncoder(fe, enc)
 
     def decode(hidden, info):  # stand-in for the host decoder: the hidden states must be complete on the GPU
-        torch.cuda.current_stream().synchronize()
+        # (runs in the plugin's decode worker thread, whose current device is not this server's: name the device)
+        torch.cuda.current_stream(hidden.device).synchronize()
         return {"text": "x", "words": []}
 
     out = {}
