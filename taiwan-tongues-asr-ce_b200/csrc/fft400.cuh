@@ -82,6 +82,64 @@ TT_HD void dft20(const float (&xr)[20], const float (&xi)[20], float (&yr)[20], 
   }
 }
 
+#if defined(__CUDACC__)
+// ---- the same transforms on packed (re, im) pairs: one FADD2 / FFMA2 / FMUL2 issue slot (sm_100 f32x2) does the real
+// and the imaginary lane of a butterfly.  138 issue slots per 20-point DFT instead of 224 (26 of them the half-swaps
+// that multiplication by -i costs in this representation).  Same arithmetic per lane as the scalar versions above.
+typedef unsigned long long c32_t;  // {re (low 32 bits), im (high)}
+__device__ __forceinline__ c32_t c_pack(float re, float im) { c32_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(re), "f"(im)); return r; }
+__device__ __forceinline__ void c_unpack(c32_t v, float& re, float& im) { asm("mov.b64 {%0, %1}, %2;" : "=f"(re), "=f"(im) : "l"(v)); }
+__device__ __forceinline__ c32_t c_add(c32_t a, c32_t b) { c32_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ c32_t c_sub(c32_t a, c32_t b) { c32_t r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ c32_t c_mul(c32_t a, c32_t b) { c32_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ c32_t c_fma(c32_t a, c32_t b, c32_t c) { c32_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ c32_t c_swap(c32_t a) { float re, im; c_unpack(a, re, im); return c_pack(im, re); }
+
+__device__ __forceinline__ void dft5_packed(c32_t& z0, c32_t& z1, c32_t& z2, c32_t& z3, c32_t& z4) {
+  const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f, s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+  const c32_t C1 = c_pack(c1, c1), C2 = c_pack(c2, c2);
+  const c32_t S1N = c_pack(s1, -s1), S2N = c_pack(s2, -s2), S1M = c_pack(-s1, s1);
+  const c32_t t1 = c_add(z1, z4), t2 = c_add(z2, z3);
+  const c32_t t3s = c_swap(c_sub(z1, z4)), t4s = c_swap(c_sub(z2, z3));   // (im, re)
+  const c32_t m1 = c_fma(C2, t2, c_fma(C1, t1, z0));
+  const c32_t m2 = c_fma(C1, t2, c_fma(C2, t1, z0));
+  // -i n1 = (n1.im, -n1.re) with n1 = s1 t3 + s2 t4;  -i n2 with n2 = s2 t3 - s1 t4
+  const c32_t n1 = c_fma(t4s, S2N, c_mul(t3s, S1N));
+  const c32_t n2 = c_fma(t4s, S1M, c_mul(t3s, S2N));
+  z0 = c_add(c_add(z0, t1), t2);
+  z1 = c_add(m1, n1);
+  z4 = c_sub(m1, n1);
+  z2 = c_add(m2, n2);
+  z3 = c_sub(m2, n2);
+}
+
+__device__ __forceinline__ void dft4_packed(c32_t& z0, c32_t& z1, c32_t& z2, c32_t& z3) {
+  const c32_t a = c_add(z0, z2), b = c_sub(z0, z2), c = c_add(z1, z3);
+  const c32_t ds = c_swap(c_sub(z1, z3));   // (d.im, d.re)
+  z0 = c_add(a, c);
+  z2 = c_sub(a, c);
+  z1 = c_fma(ds, c_pack(1.0f, -1.0f), b);   // b - i d = (b.re + d.im, b.im - d.re)
+  z3 = c_fma(ds, c_pack(-1.0f, 1.0f), b);   // b + i d
+}
+
+// forward 20-point DFT on packed pairs, natural order in -> natural order out (index maps as dft20)
+__device__ __forceinline__ void dft20_packed(const c32_t (&x)[20], c32_t (&y)[20]) {
+  c32_t u[4][5];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+#pragma unroll
+    for (int b = 0; b < 5; ++b) u[a][b] = x[(5 * a + 4 * b) % 20];
+    dft5_packed(u[a][0], u[a][1], u[a][2], u[a][3], u[a][4]);
+  }
+#pragma unroll
+  for (int kb = 0; kb < 5; ++kb) {
+    dft4_packed(u[0][kb], u[1][kb], u[2][kb], u[3][kb]);
+#pragma unroll
+    for (int ka = 0; ka < 4; ++ka) y[(5 * ka + 16 * kb) % 20] = u[ka][kb];
+  }
+}
+#endif  // __CUDACC__
+
 // power spectra of the two real frames packed as z = a + i b, from Z[k] and Z[(400-k) mod 400]
 TT_HD void split_power(float zr, float zi, float wr, float wi, float& pa, float& pb) {
   const float ar = zr + wr, ai = zi - wi;  // 2 * A[k]

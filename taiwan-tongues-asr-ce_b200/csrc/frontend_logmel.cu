@@ -170,14 +170,18 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
       {
         const float* x = &s.pcm[0];
         const int base = grp * 2 * kHop + sub;
-        float xr[20], xi[20], yr[20], yi[20];
+        float yr[20], yi[20];
+        {
+          c32_t z[20], y[20];   // frame a in the real lane, frame b in the imaginary lane: packed f32x2 butterflies
 #pragma unroll
-        for (int n1 = 0; n1 < 20; ++n1) {
-          const float w = s.win[20 * n1 + sub];
-          xr[n1] = w * load_sample<T>(x, base + 20 * n1);
-          xi[n1] = w * load_sample<T>(x, base + kHop + 20 * n1);
+          for (int n1 = 0; n1 < 20; ++n1) {
+            const float w = s.win[20 * n1 + sub];
+            z[n1] = c_pack(w * load_sample<T>(x, base + 20 * n1), w * load_sample<T>(x, base + kHop + 20 * n1));
+          }
+          dft20_packed(z, y);
+#pragma unroll
+          for (int k1 = 0; k1 < 20; ++k1) c_unpack(y[k1], yr[k1], yi[k1]);
         }
-        dft20(xr, xi, yr, yi);
         float* tr = &s.tr[grp * kTStride + sub];
         float* ti = &s.ti[grp * kTStride + sub];
         tr[0] = yr[0];
@@ -194,15 +198,17 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
       if (next < total_tiles) kind_next = stage(b_next, tt_next);
       // ---------------- pass 2: thread (grp, k1) transforms over n2 -> Z[k1 + 20 k2]
       {
-        float xr[20], xi[20], yr[20], yi[20];
+        float yr[20], yi[20];
         const float* tr = &s.tr[grp * kTStride + sub * kTRow];
         const float* ti = &s.ti[grp * kTStride + sub * kTRow];
+        {
+          c32_t z[20], y[20];
 #pragma unroll
-        for (int n2 = 0; n2 < 20; ++n2) {
-          xr[n2] = tr[n2];
-          xi[n2] = ti[n2];
+          for (int n2 = 0; n2 < 20; ++n2) z[n2] = c_pack(tr[n2], ti[n2]);
+          dft20_packed(z, y);
+#pragma unroll
+          for (int k2 = 0; k2 < 20; ++k2) c_unpack(y[k2], yr[k2], yi[k2]);
         }
-        dft20(xr, xi, yr, yi);
         __syncthreads();  // everyone has read its transpose rows; the buffer now becomes Z
         float* zr = &s.tr[grp * kTStride + sub];
         float* zi = &s.ti[grp * kTStride + sub];
