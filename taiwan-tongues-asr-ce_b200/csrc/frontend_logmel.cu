@@ -45,11 +45,20 @@ struct __align__(16) FrontSmem {
   float pcm[kSpan];                // raw samples (float, or int16 packed in the first half)
   float tr[kGroups * kTStride];    // transpose buffer (re); then Z (re); then power of the even frame
   float ti[kGroups * kTStride];    // (im);                 Z (im);       power of the odd frame
-  float2 tw[kNfft];                // W400^(n2*k1) at [k1*20 + n2]
+  float tw_re[kNfft], tw_im[kNfft];  // W400^(n2*k1) at [k1*20 + n2]: two 4-byte tables (the lanes of the second frame
+                                   // pair in a warp re-read the first one's words: a broadcast for 32-bit loads, a
+                                   // 2-way conflict per half-warp for one 64-bit load)
   float win[kNfft];
   float wmin[2][kThreads / 32];   // per-warp tile minima, double-buffered by tile parity (see the reduction)
   unsigned long long bar;
 };
+
+// column of frame f (0..31) inside a [bin][32 frames] power-spectrum row: a bijection with pw_col(2g + 2) - pw_col(2g) = 20
+// (mod 32) except across g = 7 -> 8, and pw_col(2g + 1) = pw_col(2g) + 1
+__device__ __forceinline__ int pw_col(int f) {
+  const int g = f >> 1;
+  return ((20 * g) & 31) + ((g >> 3) << 1) + (f & 1);
+}
 
 template <typename T>
 __device__ __forceinline__ float load_sample(const float* buf, int i);
@@ -89,7 +98,9 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
 
   // ---- one-time tables -> shared memory
   for (int i = tid; i < kNfft; i += kThreads) {
-    s.tw[i] = tables.twiddle[i];
+    const float2 w = tables.twiddle[i];
+    s.tw_re[i] = w.x;
+    s.tw_im[i] = w.y;
     s.win[i] = tables.window[i];
   }
   const uint32_t bar = smem_u32(&s.bar);
@@ -188,7 +199,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         ti[0] = yi[0];
 #pragma unroll
         for (int k1 = 1; k1 < 20; ++k1) {
-          const float2 w = s.tw[k1 * 20 + sub];
+          const float2 w = make_float2(s.tw_re[k1 * 20 + sub], s.tw_im[k1 * 20 + sub]);
           tr[k1 * kTRow] = yr[k1] * w.x - yi[k1] * w.y;
           ti[k1 * kTRow] = yr[k1] * w.y + yi[k1] * w.x;
         }
@@ -237,7 +248,9 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
           }
         }
         __syncthreads();  // all Z reads done; the (re) buffer now holds the power spectra
-        float* pw = &s.tr[2 * grp];
+        // frame f of the tile sits in COLUMN pw_col(f) of its bin row: consecutive frame pairs are 20 columns apart (mod 32),
+        // so the two pairs whose threads share a warp write disjoint banks; the mel pass reads column pw_col(lane)
+        float* pw = &s.tr[pw_col(2 * grp)];
 #pragma unroll
         for (int i = 0; i < 11; ++i) {
           const int k = sub + kRadix * i;
@@ -258,7 +271,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         int m = mel.m0[wrp];
         float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
         __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
-        const unsigned char* pw = reinterpret_cast<const unsigned char*>(&s.tr[lane]);
+        const unsigned char* pw = reinterpret_cast<const unsigned char*>(&s.tr[pw_col(lane)]);
         float acc_a = 0.f, acc_b = 0.f;
         const int op_end = mel.op_off[wrp + 1];
         for (int oi = mel.op_off[wrp]; oi < op_end; ++oi) {
