@@ -91,6 +91,11 @@ TTASR_API int ttasr_frontend_run_ex(const ttasr_frontend_t* h, const void* pcm_d
                           int tmajor_ld, float clamp_decades, void* stream);
 /* largest batch one ttasr_frontend_run call accepts (sizes the handle's scratch: per-chunk maxima, per-tile minima) */
 TTASR_API int ttasr_frontend_max_batch(const ttasr_frontend_t* h, int64_t* out);
+/* which mel projection the handle runs: 80 = the straight-line code compiled in for the 80-filter Whisper bank (chosen
+ * when mel_filters is bit-identical to the HF table: audio_utils.py:453-544 with 80 slaney triangles, 16 kHz, n_fft 400),
+ * 0 = the generic per-bin program built from mel_filters (any bank of overlapping triangles, incl. the 128-filter one;
+ * also forced by TTASR_FRONTEND_MEL=generic in the environment at create time).  Both give bit-identical features. */
+TTASR_API int ttasr_frontend_mel_mode(const ttasr_frontend_t* h, int* out);
 TTASR_API void ttasr_frontend_destroy(ttasr_frontend_t* h);
 
 /* ------------------------------------------------------------------ ingest (step before the path) ---

@@ -34,7 +34,7 @@ def _digest() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for name in sorted(os.listdir(root)):
-            if name.endswith((".cu", ".cuh", ".h")):
+            if name.endswith((".cu", ".cuh", ".h", ".inc")):
                 with open(os.path.join(root, name), "rb") as f:
                     h.update(name.encode())
                     h.update(f.read())

@@ -156,6 +156,15 @@ __device__ __forceinline__ void exp2_poly_pair(uint32_t& a, uint32_t& b) {
   b = __float_as_uint(p1) + (__float_as_uint(t1) << 23);
 }
 
+// TTASR_ATTN_LATEMAX=1 (experiment, measured slower — DESIGN.md 4.3): only quarter 0's own maximum is taken before the
+// sweep starts; the maximum of the other three quarters is computed on the ALU pipe BESIDE quarter 0's exponentials
+// (which run against the previous base), the base is corrected afterwards in the rare case it has to move, and the
+// o_done wait moves behind quarter 0.  The in-kernel timeline shows the same chain length: the steps it removes
+// (row max 390 -> 207 cycles, o_done wait) come back as the longer quarter 0 and the extra checks.
+#ifndef TTASR_ATTN_LATEMAX
+#define TTASR_ATTN_LATEMAX 0
+#endif
+
 // POLY8: of every 8 consecutive scores of the chunk, the first POLY8 (even) take the polynomial, the rest MUFU.EX2
 template <int POLY8>
 __device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], float m_used) {
@@ -183,6 +192,37 @@ __device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], float m_used) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(ex2(fmaf(__uint_as_float(v[i]), kLog2e, -m_used)));
 #endif
+}
+// exp_inplace over v, interleaved with the maximum over three other chunks (independent work for the ALU pipe while
+// the exponentials occupy the MUFU pipe)
+template <int POLY8>
+__device__ __forceinline__ float exp_inplace_max3(uint32_t (&v)[32], float m_used, const uint32_t (&a)[32],
+                                                  const uint32_t (&b)[32], const uint32_t (&c)[32]) {
+  const float neg_m = -m_used;
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < 32; i += 2) {
+    asm("{ .reg .b64 t, u, w;\n\t"
+        "mov.b64 t, {%0, %1};\n\t"
+        "mov.b64 u, {%2, %2};\n\t"
+        "mov.b64 w, {%3, %3};\n\t"
+        "fma.rn.f32x2 t, t, u, w;\n\t"
+        "mov.b64 {%0, %1}, t; }"
+        : "+r"(v[i]), "+r"(v[i + 1])
+        : "r"(__float_as_uint(kLog2e)), "r"(__float_as_uint(neg_m)));
+    if ((i & 7) < POLY8) {
+      exp2_poly_pair(v[i], v[i + 1]);
+    } else {
+      v[i] = __float_as_uint(ex2(__uint_as_float(v[i])));
+      v[i + 1] = __float_as_uint(ex2(__uint_as_float(v[i + 1])));
+    }
+    // three 3-input maxima per pair of exponentials, two dependency chains
+    m0 = fmaxf(m0, fmaxf(__uint_as_float(a[i]), __uint_as_float(a[i + 1])));
+    m1 = fmaxf(m1, fmaxf(__uint_as_float(b[i]), __uint_as_float(b[i + 1])));
+    if (i & 2) m0 = fmaxf(m0, fmaxf(__uint_as_float(c[i]), __uint_as_float(c[i + 1])));
+    else m1 = fmaxf(m1, fmaxf(__uint_as_float(c[i]), __uint_as_float(c[i + 1])));
+  }
+  return fmaxf(m0, m1);
 }
 __device__ __forceinline__ float sum_pack(const uint32_t (&v)[32], uint32_t (&pk)[16]) {
 #if TTASR_ATTN_F32X2
@@ -462,34 +502,62 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           mask_tail(v2, 64, last_valid);
           mask_tail(v3, 96, last_valid);
         }
+        // PV_t(j-1) (issued a sweep ago) must have consumed P_t and left O_t quiescent before either is written again.
+        bool o_waited = (j == 0);
+        auto wait_o = [&]() {
+          if (!o_waited) {
+            mbar_wait(smem_u32(&s.o_done[t]), ophase);
+            ophase ^= 1;
+            tc_fence_after();
+            o_waited = true;
+          }
+        };
+        // move the exponent base to m_new: l, O (and, with fix_q0, the already exponentiated quarter 0) shrink by 2^(old - new)
+        auto rebase = [&](float m_new, bool fix_q0) {
+          const float factor = ex2(m_used - m_new);
+          m_used = m_new;
+          l *= factor;
+          if (fix_q0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v0[i] = __float_as_uint(__uint_as_float(v0[i]) * factor);
+          }
+          if (j > 0) {
+            wait_o();
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+              uint32_t o[32];
+              tmem_ld_32x32(o_addr + c * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
+              tmem_st_32x32(o_addr + c * 32, o);
+            }
+          }
+        };
+#if TTASR_ATTN_LATEMAX
+        // quarter 0's own maximum decides whether its exponentials may run against the current base (never above
+        // 2^threshold); the rest of the row maximum is taken beside them (exp_inplace_max3) and checked afterwards
+        const float m_q0 = chunk_max(v0) * kLog2e;
+        tr(13);
+        if (j == 0) {
+          m_used = m_q0;
+        } else if (__any_sync(0xffffffffu, (m_q0 - m_used) > kRescaleThreshold)) {  // rare
+          rebase(fmaxf(m_used, m_q0), false);
+        }
+        tr(14);
+#else
         const float mx = fmaxf(fmaxf(chunk_max(v0), chunk_max(v1)), fmaxf(chunk_max(v2), chunk_max(v3)));
         const float m_tile = mx * kLog2e;
         tr(13);
-        // PV_t(j-1) (issued a sweep ago) must have consumed P_t and left O_t quiescent before either is written again.
         // (Deferring this wait into the sweep was measured slower: it then sits inside the token-exclusive section.)
-        if (j > 0) {
-          mbar_wait(smem_u32(&s.o_done[t]), ophase);
-          ophase ^= 1;
-          tc_fence_after();
-        }
+        wait_o();
         tr(14);
         if (j == 0) {
           m_used = m_tile;
         } else if (__any_sync(0xffffffffu, (m_tile - m_used) > kRescaleThreshold)) {  // rare
-          const float m_new = fmaxf(m_used, m_tile);
-          const float factor = ex2(m_used - m_new);
-          m_used = m_new;
-          l *= factor;
-#pragma unroll 1
-          for (int c = 0; c < 2; ++c) {
-            uint32_t o[32];
-            tmem_ld_32x32(o_addr + c * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * factor);
-            tmem_st_32x32(o_addr + c * 32, o);
-          }
+          rebase(fmaxf(m_used, m_tile), false);
         }
+#endif
         // ---- exp sweep.  The first kPreTokenChunks quarter(s) run beside the other warpgroup's sweep (one warp per
         // scheduler cannot quite saturate the 16-op/clk exp pipe); the rest is exclusive (token), so the pipe never
         // idles while this warpgroup waits for / reads its next S tile.  The exponentials go back over the scores in
@@ -509,7 +577,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         };
         auto tok_acquire = [&]() { tr(15); asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory"); tr(16); };
         if (kPreTokenChunks == 0) tok_acquire();
+#if TTASR_ATTN_LATEMAX
+        {
+          const float m_rest = exp_inplace_max3<TTASR_ATTN_POLY_Q0>(v0, m_used, v1, v2, v3) * kLog2e;
+          if (__any_sync(0xffffffffu, (m_rest - m_used) > kRescaleThreshold)) rebase(fmaxf(m_used, m_rest), true);  // rare
+          tr(19);
+          wait_o();   // long complete by now: P_t may be overwritten from here on
+        }
+#else
         stage_a(v0, 0);
+#endif
         if (kPreTokenChunks == 1) tok_acquire();
         stage_a(v1, 1);
         stage_b(v0, 0);

@@ -81,7 +81,41 @@ __device__ __forceinline__ float dec_ordered(unsigned u) {
 constexpr float kYFloor = -1.5f;                         // (log10(1e-10) + 4) / 4
 constexpr float kLog2ToY = 0.25f * 0.30102999566398120f; // y = log2(p) * log10(2) / 4 + 1
 
-template <typename T>
+// (log10(max(acc, 1e-10)) + 4) / 4 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate; acc > 1e-10 is a normal
+// number, so the flush-to-zero form needs no denormal path); the floor is returned exactly
+__device__ __forceinline__ float mel_to_y(float acc) {
+  float lg;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(acc));
+  return acc > kMelFloor ? fmaf(lg, kLog2ToY, 1.0f) : kYFloor;
+}
+
+// Sink of the baked mel code (mel_baked.inc): filters complete in ascending order and are written out in pairs
+// (m even, m + 1): two fp32 stores along time (lane = frame), one packed bf16x2 word of the time-major staging row.
+// RAW: 0 = no fp32 output, 1 = every lane of the warp stores (the tile lies inside the chunk), 2 = lanes past the last
+// frame do not (last tile of a chunk) — a warp-uniform choice, so the common paths carry no per-lane branches.
+template <int RAW>
+struct MelEmit {
+  float* out;          // &raw[b][0][t0 + lane]
+  long long nf;        // n_frames
+  uint32_t* stg;       // the lane's staging row (bf16 pairs)
+  float vmax, vmin;    // over everything this lane emitted (the caller discards them for lanes past the last frame)
+  bool live;
+  __device__ __forceinline__ float y(float acc) const { return mel_to_y(acc); }
+  __device__ __forceinline__ void emit2(int m, float y0, float y1) {
+    if (RAW == 1 || (RAW == 2 && live)) {
+      out[m * nf] = y0;
+      out[(m + 1) * nf] = y1;
+    }
+    vmax = fmaxf(vmax, fmaxf(y0, y1));
+    vmin = fminf(vmin, fminf(y0, y1));
+    stg[m >> 1] = pack_bf16x2(y0, y1);
+  }
+};
+
+#include "mel_baked.inc"
+
+// MELB: 0 = generic mel program (any bank of overlapping triangles); 80 = the baked 80-filter Whisper bank (mel_baked.inc)
+template <typename T, int MELB>
 __global__ void __launch_bounds__(kThreads, 2)
 logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int* __restrict__ n_valid, int n_samples,
                      int n_frames, int n_mels, int batch, FrontTables tables, const __grid_constant__ MelProgram mel,
@@ -268,6 +302,25 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         const int lane = tid & 31;
         const int wrp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: constant-bank indexing
         const bool live = (t0 + lane) < n_frames;
+        if constexpr (MELB != 0) {
+          // the bank is known at compile time: straight-line LDS + FFMA per bin, weights and offsets as immediates
+          auto run = [&](auto o) {
+            o.out = raw + static_cast<long long>(b) * MELB * n_frames + t0 + lane;
+            o.nf = n_frames;
+            o.stg = reinterpret_cast<uint32_t*>(&s.ti[0]) + lane * ((tmajor_ld >> 1) + 1);   // ti is idle by now
+            o.vmax = -INFINITY;
+            o.vmin = INFINITY;
+            o.live = live;
+            MelBaked<MELB>::run(wrp, &s.tr[pw_col(lane)], o);
+            if (live) {
+              tmax = fmaxf(tmax, o.vmax);
+              tmin = fminf(tmin, o.vmin);
+            }
+          };
+          if (raw == nullptr) run(MelEmit<0>{});
+          else if (t0 + kTileFrames <= n_frames) run(MelEmit<1>{});
+          else run(MelEmit<2>{});
+        } else {
         int m = mel.m0[wrp];
         float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
         __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
@@ -280,11 +333,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
           acc_a = fmaf(__int_as_float(op.y), p, acc_a);
           acc_b = fmaf(__int_as_float(op.z), p, acc_b);
           if (op.w) {  // filter complete
-            // (log10 + 4) / 4 through the hardware lg2 (abs err ~1e-7 << the 1e-4 gate; acc_a > 1e-10 is a normal
-            // number, so the flush-to-zero form needs no denormal path); the floor is returned exactly
-            float lg;
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(acc_a));
-            const float v = acc_a > kMelFloor ? fmaf(lg, kLog2ToY, 1.0f) : kYFloor;
+            const float v = mel_to_y(acc_a);
             if (live) {
               if (raw) *out_ptr = v;
               tmax = fmaxf(tmax, v);
@@ -296,6 +345,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
             out_ptr += n_frames;
             ++stg;
           }
+        }
         }
       }
       __syncthreads();  // power spectra consumed before the next tile's pass 1 overwrites the buffer; staging complete
@@ -316,11 +366,9 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
       }
     }
     // ---------------- tile max -> chunk max (one atomic per warp); tile min -> table (one store per tile)
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, o));
-      tmin = fminf(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
-    }
+    // (one REDUX each on the order-preserving integer encoding instead of a five-step shuffle tree)
+    tmax = dec_ordered(__reduce_max_sync(0xffffffffu, enc_ordered(tmax)));
+    tmin = dec_ordered(__reduce_min_sync(0xffffffffu, enc_ordered(tmin)));
     // (double-buffered: a padding tile reaches this point without any block barrier, so the other warps may already
     // be writing the NEXT tile's minima while thread 0 still reads this tile's)
     if ((tid & 31) == 0) {
@@ -395,39 +443,44 @@ logmel_clamp_kernel(float* __restrict__ feats, const unsigned* __restrict__ chun
 }  // namespace
 
 size_t frontend_smem_bytes() { return sizeof(FrontSmem); }
+unsigned long long frontend_baked_hash(int n_mels) { return n_mels == 80 ? MelBaked<80>::kHash : 0ull; }
 int frontend_tiles(int n_samples) { return (n_samples / kHop + kTileFrames - 1) / kTileFrames; }
 
 cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
                           int n_mels, int batch, const FrontTables& tables, const MelProgram& mel, float* feats, unsigned* chunk_max,
                           float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream,
-                          float clamp_decades) {
+                          float clamp_decades, int mel_baked) {
   const int n_frames = n_samples / kHop;
   const int tiles_per_chunk = (n_frames + kTileFrames - 1) / kTileFrames;
   const long long total = static_cast<long long>(batch) * tiles_per_chunk;
   if (total == 0) return cudaSuccess;
   const size_t smem = sizeof(FrontSmem);
-  static PerDeviceOnce attr_set;
-  if (attr_set.need()) {
-    cudaError_t e = cudaFuncSetAttribute(logmel_frames_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(logmel_frames_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
   if (tmajor && static_cast<size_t>(kTileFrames) * (tmajor_ld + 2) * sizeof(__nv_bfloat16) > sizeof(FrontSmem::ti))
     return cudaErrorInvalidValue;
+  if (mel_baked != 0 && mel_baked != n_mels) return cudaErrorInvalidValue;
   {
     cudaError_t e = cudaMemsetAsync(chunk_max, 0, sizeof(unsigned) * batch, stream);  // 0 < enc_ordered(any float)
     if (e != cudaSuccess) return e;
   }
   const int grid = static_cast<int>(total < 2LL * num_sms ? total : 2LL * num_sms);
-  if (pcm_is_i16)
-    logmel_frames_kernel<int16_t><<<grid, kThreads, smem, stream>>>(static_cast<const int16_t*>(pcm), row_stride, n_valid,
-                                                                   n_samples, n_frames, n_mels, batch, tables, mel, feats,
-                                                                   chunk_max, tile_min, tmajor, tmajor_ld);
+  auto launch = [&](auto kern, PerDeviceOnce& once, const auto* in) -> cudaError_t {
+    if (once.need()) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+    }
+    kern<<<grid, kThreads, smem, stream>>>(in, row_stride, n_valid, n_samples, n_frames, n_mels, batch, tables, mel, feats,
+                                           chunk_max, tile_min, tmajor, tmajor_ld);
+    return cudaSuccess;
+  };
+  static PerDeviceOnce once[4];
+  cudaError_t le;
+  const float* pf = static_cast<const float*>(pcm);
+  const int16_t* pi = static_cast<const int16_t*>(pcm);
+  if (mel_baked == 80)
+    le = pcm_is_i16 ? launch(logmel_frames_kernel<int16_t, 80>, once[0], pi) : launch(logmel_frames_kernel<float, 80>, once[1], pf);
   else
-    logmel_frames_kernel<float><<<grid, kThreads, smem, stream>>>(static_cast<const float*>(pcm), row_stride, n_valid,
-                                                                 n_samples, n_frames, n_mels, batch, tables, mel, feats,
-                                                                 chunk_max, tile_min, tmajor, tmajor_ld);
+    le = pcm_is_i16 ? launch(logmel_frames_kernel<int16_t, 0>, once[2], pi) : launch(logmel_frames_kernel<float, 0>, once[3], pf);
+  if (le != cudaSuccess) return le;
   dim3 g2((tiles_per_chunk + kClampTiles - 1) / kClampTiles, batch);
   logmel_clamp_kernel<<<g2, 256, 0, stream>>>(feats, chunk_max, tile_min, n_frames, n_mels, tiles_per_chunk, tmajor,
                                               tmajor_ld, clamp_decades * 0.25f);

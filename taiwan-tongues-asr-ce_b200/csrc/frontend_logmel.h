@@ -35,7 +35,10 @@ size_t frontend_smem_bytes();
 cudaError_t launch_logmel(const void* pcm, int pcm_is_i16, long long row_stride, const int* n_valid, int n_samples,
                           int n_mels, int batch, const FrontTables& tables, const MelProgram& mel, float* feats, unsigned* chunk_max,
                           float* tile_min, __nv_bfloat16* tmajor, int tmajor_ld, int num_sms, cudaStream_t stream,
-                          float clamp_decades = 8.0f);
+                          float clamp_decades = 8.0f, int mel_baked = 0);
+// FNV-1a 64 hash of the fp32 [201, n_mels] filter table whose projection is compiled into the kernel (mel_baked.inc:
+// the two Whisper banks), 0 if there is none for this n_mels; launch_logmel(mel_baked = n_mels) selects that code.
+unsigned long long frontend_baked_hash(int n_mels);
 // scratch the caller provides: chunk_max[batch] (order-encoded running maxima), tile_min[batch * frontend_tiles(n_samples)]
 int frontend_tiles(int n_samples);
 

@@ -25,6 +25,7 @@
 //               LayerNorm statistics of out_hi                             (split residual stream, the default)
 #include "gemm_sm100.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <unordered_map>
@@ -727,6 +728,11 @@ cudaError_t gemm_launch(const GemmCall& c, int num_sms, cudaStream_t stream, con
     auto tiles = [&](int bn_, int cg_) {
       return static_cast<long long>((c.rows + kBM * cg_ - 1) / (kBM * cg_)) * c.nbatch * (c.n / bn_);
     };
+    // (Measured and dropped, round 2: picking the shape by rounds x tile time instead — more, smaller tiles when the
+    // large ones leave a ragged last wave — lost at B = 1 / 2 (3.58 -> 3.68 ms, 5.32 -> 6.07 ms per large-v3 forward):
+    // at M = 1500 the GEMMs are bound by L2 -> SM operand traffic, which grows as 1/BN + 1/BM, not by the tail.  Lowering
+    // the 0.6 threshold to 0.4 (256-wide pairs for the N = 1280 GEMMs at B = 1: 30 tiles on 74 pairs) lost as well:
+    // out-proj 17.9 -> 21.1 us, fc2 35.0 -> 39.5 us.)
     const int cand[3][2] = {{bn, 2}, {128, 2}, {128, 1}};
     for (int i = 0; i < 3; ++i) {
       bn = cand[i][0];

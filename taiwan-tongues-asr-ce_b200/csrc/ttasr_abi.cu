@@ -133,6 +133,7 @@ struct ttasr_frontend {
   int n_samples = 0;
   FrontTables tables{};
   MelProgram mel{};               // host copy: passed to the frames kernel as a parameter (constant bank)
+  int mel_baked = 0;              // n_mels when the bank equals one compiled into the kernel (mel_baked.inc), else 0
   void* table_mem = nullptr;
   unsigned* chunk_max = nullptr;  // per-chunk running maxima (order-encoded), capacity max_batch
   float* tile_min = nullptr;      // per-tile minima, capacity max_batch * tiles per chunk
@@ -251,6 +252,14 @@ int ttasr_frontend_create(int n_mels, int n_fft, int hop, int n_samples, const f
   memcpy(h->mel.ops, ops.data(), sizeof(int4) * kMaxMelOps);
   memcpy(h->mel.op_off, op_off.data(), sizeof(int) * (kMelWarps + 1));
   memcpy(h->mel.m0, warp_m0.data(), sizeof(int) * (kMelWarps + 1));
+  {  // the two Whisper banks have their projection compiled into the kernel; any other table runs the program above
+    unsigned long long hash = 0xcbf29ce484222325ull;  // FNV-1a 64 over the bytes of the fp32 table
+    const unsigned char* bytes_in = reinterpret_cast<const unsigned char*>(mel_filters);
+    for (size_t i = 0; i < sizeof(float) * kNfreq * static_cast<size_t>(n_mels); ++i) hash = (hash ^ bytes_in[i]) * 0x100000001b3ull;
+    const char* force = getenv("TTASR_FRONTEND_MEL");
+    const bool generic = force && !strcmp(force, "generic");
+    if (!generic && frontend_baked_hash(n_mels) != 0ull && hash == frontend_baked_hash(n_mels)) h->mel_baked = n_mels;
+  }
   const size_t bytes = sizeof(float2) * kNfft + sizeof(float) * kNfft;
   cudaError_t e = cudaMalloc(&h->table_mem, bytes);
   if (e != cudaSuccess) { delete h; return fail(TTASR_E_NOMEM, "frontend_create: cudaMalloc tables: %s", cudaGetErrorString(e)); }
@@ -284,6 +293,12 @@ int ttasr_frontend_max_batch(const ttasr_frontend_t* h, int64_t* out) {
   return TTASR_OK;
 }
 
+int ttasr_frontend_mel_mode(const ttasr_frontend_t* h, int* out) {
+  if (!h || !out) return fail(TTASR_E_ARG, "frontend_mel_mode: null argument");
+  *out = h->mel_baked;
+  return TTASR_OK;
+}
+
 int ttasr_frontend_run(const ttasr_frontend_t* h, const void* pcm_dev, int pcm_dtype, int64_t batch, int64_t row_stride,
                        const int32_t* n_valid_dev, float* feats_dev, void* tmajor_dev, int tmajor_ld, void* stream) {
   return ttasr_frontend_run_ex(h, pcm_dev, pcm_dtype, batch, row_stride, n_valid_dev, feats_dev, tmajor_dev, tmajor_ld,
@@ -305,7 +320,7 @@ int ttasr_frontend_run_ex(const ttasr_frontend_t* h, const void* pcm_dev, int pc
   cudaError_t e = launch_logmel(pcm_dev, pcm_dtype == TTASR_PCM_I16, row_stride, n_valid_dev, h->n_samples, h->n_mels,
                                 static_cast<int>(batch), h->tables, h->mel, feats_dev, h->chunk_max, h->tile_min,
                                 static_cast<__nv_bfloat16*>(tmajor_dev), tmajor_ld, h->num_sms,
-                                static_cast<cudaStream_t>(stream), clamp_decades);
+                                static_cast<cudaStream_t>(stream), clamp_decades, h->mel_baked);
   if (e != cudaSuccess) return fail(TTASR_E_CUDA, "frontend_run: launch failed: %s", cudaGetErrorString(e));
   return TTASR_OK;
 }

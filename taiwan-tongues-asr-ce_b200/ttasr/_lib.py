@@ -54,6 +54,7 @@ PROTOTYPES = {
     "ttasr_frontend_run_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_float, C.c_void_p]),
     "ttasr_frontend_max_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    "ttasr_frontend_mel_mode": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "ttasr_frontend_destroy": (None, [C.c_void_p]),
     "ttasr_ingest_create": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "ttasr_ingest_out_len": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),

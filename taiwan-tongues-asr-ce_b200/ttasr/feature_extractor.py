@@ -94,6 +94,14 @@ class B200WhisperFeatureExtractor:
             self._handles[idx] = h
         return h
 
+    def mel_mode(self, dev=None) -> int:
+        """80: the native front end runs the mel projection compiled in for the 80-filter Whisper bank (chosen when
+        `mel_filters` is bit-identical to the table baked into the kernel); 0: the generic program built from
+        `mel_filters` (every other bank, the 128-filter one included).  Same features either way."""
+        out = C.c_int()
+        _lib.check(_lib.lib().ttasr_frontend_mel_mode(self._native(dev), C.byref(out)))
+        return int(out.value)
+
     def __del__(self):
         handles, self._handles = getattr(self, "_handles", {}), {}
         for h in handles.values():

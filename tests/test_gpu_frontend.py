@@ -201,3 +201,43 @@ def test_matches_the_torch_extractor_the_reference_dispatches_to(cuda_device, n_
     # and through the public call surface, the way train_asr.py:607-616 uses it (batched per-row max, a4 semantics)
     out = hf(list(clips), sampling_rate=16000, return_tensors="np")["input_features"]
     assert float(np.abs(got - out).max()) <= 1.5e-4
+
+
+def test_compiled_in_mel_projection_is_selected_and_bit_equal_to_the_generic_program(cuda_device, monkeypatch):
+    """The 80-filter Whisper bank runs straight-line mel code generated at build time (csrc/mel_baked.inc); the generic
+    per-bin program (any bank; forced with TTASR_FRONTEND_MEL=generic) accumulates in the same order, so both must give
+    the same bits: fp32 features and the bf16 time-major copy, f32 and int16 PCM, full tiles, the partial last tile and
+    n_valid padding."""
+    import torch
+
+    clips = np.stack([OF.pad_or_trim(f()) for f in (OF.synth_noise, OF.synth_tones, OF.synth_short)])
+    pcm = torch.from_numpy(clips).to(cuda_device)
+    pcm_i16 = (pcm * 20000).to(torch.int16)
+    nv = torch.tensor([480000, 300001, 48000], dtype=torch.int32, device=cuda_device)
+    n_mels = 80
+    assert _fe(128).mel_mode() == 0   # the 128-filter bank stays on the program (instruction-cache footprint, DESIGN 4.1)
+    baked = _fe(n_mels)
+    assert baked.mel_mode() == n_mels, "the standard bank did not select the compiled-in projection"
+    monkeypatch.setenv("TTASR_FRONTEND_MEL", "generic")
+    generic = _fe(n_mels)
+    assert generic.mel_mode() == 0
+    for x, kw in ((pcm, {}), (pcm_i16, {}), (pcm, {"n_valid": nv})):
+        fa, ta = baked.extract(x, return_time_major=True, **kw)
+        fb, tb = generic.extract(x, return_time_major=True, **kw)
+        assert torch.equal(fa, fb) and torch.equal(ta, tb)
+        _, tc = baked.extract(x, return_time_major=True, features=False, **kw)
+        assert torch.equal(tc, ta)
+
+
+def test_generic_mel_program_on_a_non_whisper_bank(cuda_device):
+    """Any other bank of overlapping triangles (here 64 filters) runs the host-built program."""
+    import torch
+
+    clips = [OF.pad_or_trim(f()) for f in (OF.synth_noise, OF.synth_tones, OF.synth_short)]
+    pcm = torch.from_numpy(np.stack(clips)).to(cuda_device)
+    fe = _fe(64)
+    assert fe.mel_mode() == 0
+    got = fe.extract(pcm).cpu().numpy()
+    for i, c in enumerate(clips):
+        err = np.abs(got[i] - OF.log_mel(c, 64)).max()
+        assert err <= TOL, f"clip {i}: max abs err {err}"

@@ -113,6 +113,32 @@ def test_attention_large_logits_trigger_rescale(cuda_device):
     assert (out.float() - ref).abs().max().item() <= 3e-2
 
 
+def test_attention_base_moves_at_every_point_of_the_sweep(cuda_device):
+    """Spike keys placed so that the exponent base has to move (a) in the first key tile after quarter 0 has already been
+    exponentiated, (b) in a later tile by a key outside quarter 0, (c) in a later tile by a key inside quarter 0, each by
+    far more than the lazy-rescale threshold; rows whose q points the other way see the spikes as very negative scores."""
+    import torch
+
+    L = _lib()
+    B, T, H, d = 2, 700, 2, 64
+    g = torch.Generator(device=cuda_device).manual_seed(7)
+    q = torch.randn((B, T, H, d), generator=g, device=cuda_device) * 0.5
+    q[..., 0] += 1.0
+    k = torch.randn((B, T, H, d), generator=g, device=cuda_device)
+    v = torch.randn((B, T, H, d), generator=g, device=cuda_device)
+    for idx, amp in ((40, 60.0), (2 * 128 + 100, 120.0), (4 * 128 + 5, 180.0)):
+        k[:, idx] = 0.0
+        k[:, idx, :, 0] = amp
+    qkv = torch.cat([t.reshape(B, T, H * d) for t in (q, k, v)], dim=-1).to(torch.bfloat16)
+    out = torch.full((B, T, H * d), float("nan"), dtype=torch.bfloat16, device=cuda_device)
+    L.check(L.lib().ttasr_op_attention(qkv.data_ptr(), out.data_ptr(), B, T, H, _stream(torch, cuda_device)))
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().view(B, T, H, d).transpose(1, 2) for t in qkv.split(H * d, dim=-1))
+    ref = (torch.softmax(qf @ kf.transpose(2, 3), dim=-1) @ vf).transpose(1, 2).reshape(B, T, H * d)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() <= 3e-2
+
+
 def test_bad_arguments_surface_as_errors(cuda_device):
     import torch
 

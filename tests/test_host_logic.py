@@ -182,3 +182,22 @@ def test_asr_plugin_microbatcher_batches_concurrent_clients():
     assert all(r["final"] and r["language"] == "zh" and set(r) == {"language", "language_probability", "final",
                                                                     "text", "duration", "words"} for r in results)
     assert pcm_bytes_to_tensor(bytearray(b"\x01\x00\xff\xff\x05")).tolist() == [1, -1]
+
+
+def test_generated_mel_code_is_current():
+    """csrc/mel_baked.inc (committed) is what csrc/gen_mel_baked.py generates from ttasr/mel.py today, and its hashes are
+    those of the tables the Python extractor hands to ttasr_frontend_create."""
+    import importlib.util
+    import os
+
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "taiwan-tongues-asr-ce_b200", "csrc")
+    spec = importlib.util.spec_from_file_location("gen_mel_baked", os.path.join(csrc, "gen_mel_baked.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    with open(os.path.join(csrc, "mel_baked.inc")) as f:
+        assert f.read() == gen.generate()
+    from ttasr import B200WhisperFeatureExtractor
+
+    for n_mels in gen.BANKS:
+        table = np.ascontiguousarray(B200WhisperFeatureExtractor(feature_size=n_mels).mel_filters, dtype=np.float32)
+        assert f"0x{gen.fnv1a64(table.tobytes()):016x}ull" in gen.gen_bank(n_mels)

@@ -14,7 +14,7 @@ import torch  # noqa: E402
 NAMES = {10: "loop_top", 11: "s_full_ok", 12: "ldtm_done", 13: "max_done", 14: "odone_ok", 15: "pre_done", 16: "token_ok",
          17: "sweep_done", 18: "p_ready_sent", 30: "wait_p0", 31: "wait_p1", 32: "got_p0", 33: "got_p1", 40: "wait_sf0",
          41: "wait_sf1", 42: "got_sf0", 43: "got_sf1", 44: "wait_kv", 45: "got_kv", 50: "wait_kvfree", 51: "got_kvfree",
-         19: "a1_done", 60: "pv_begin", 61: "pv_mma1", 62: "pv_mma4", 63: "pv_mma8", 64: "pv_commit", 65: "pv_end", 20: "epi_wait", 21: "epi_go", 22: "epi_done"}
+         19: "q0_done", 60: "pv_begin", 61: "pv_mma1", 62: "pv_mma4", 63: "pv_mma8", 64: "pv_commit", 65: "pv_end", 20: "epi_wait", 21: "epi_go", 22: "epi_done"}
 
 
 def main():

@@ -12,8 +12,17 @@ sys.path.insert(0, PKG)
 import build as B  # noqa: E402
 
 V4 = "TTASR_ATTN_DEFAULT_VARIANT=4"
+LM = "TTASR_ATTN_LATEMAX=1"
 VARIANTS = {
-    "v2": [],                                   # two softmax warpgroups, 128-key tiles (attention_sm100.cu)
+    "v2": [],                                   # two softmax warpgroups, 128-key tiles (attention_sm100.cu), as shipped
+    "base": ["TTASR_ATTN_LATEMAX=0"],           # ... with the whole row max taken before the sweep (the round-1 chain)
+    "lm": [LM],                                 # quarter-0 max first, the rest beside quarter 0's exponentials
+    "lm_n": [LM, "TTASR_ATTN_SETMAXNREG=1"],    # ... softmax warps at 224 registers
+    "lm_p2": [LM, "TTASR_ATTN_PRETOKEN=2"],     # ... two quarters outside the token
+    "lm_p2n": [LM, "TTASR_ATTN_PRETOKEN=2", "TTASR_ATTN_SETMAXNREG=1"],
+    "lm_q2": [LM, "TTASR_ATTN_POLY_Q0=2"],      # ... a quarter of quarter 0's exponentials on the FMA pipe
+    "lm_p2q2": [LM, "TTASR_ATTN_PRETOKEN=2", "TTASR_ATTN_POLY_Q0=2", "TTASR_ATTN_POLY_Q1=2"],
+    "lm_q4": [LM, "TTASR_ATTN_POLY_Q0=4"],      # ... half of quarter 0
     "v4": [V4],                                 # four softmax warpgroups, 64-key steps (attention4_sm100.cu)
     "v4p2": [V4, "TTASR_ATTN4_POLY8=2"],        # ... a quarter of the exponentials on the FMA pipe
     "v4p4": [V4, "TTASR_ATTN4_POLY8=4"],        # ... half

@@ -22,7 +22,8 @@ def main():
     pipe = ttasr.B200LogMelEncoder(fe, enc)
     enc.reserve_workspace(32)  # captured graphs bake the workspace address in: size it once for the largest batch
     out = {}
-    for B in (1, 2, 4, 8, 16, 32):
+    batches = tuple(int(a) for a in sys.argv[1:] if a.isdigit()) or (1, 2, 4, 8, 16, 32)
+    for B in batches:
         pcm = (torch.randn((B, 80000), device=dev) * 3000).to(torch.int16)  # 5 s utterances, int16 wire format
         nv = torch.full((B,), 80000, dtype=torch.int32, device=dev)
 
@@ -50,10 +51,21 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(); g.replay(); b.record(); torch.cuda.synchronize()
             tg.append(a.elapsed_time(b))
+        stages = None
+        if B in (1, 8):  # where the time goes, eager (CUDA events around every launch, so the sum exceeds the graph time)
+            enc.profile(True); enc.profile_read(reset=True)
+            for _ in range(10):
+                run()
+            torch.cuda.synchronize()
+            stages = {k: {"us_per_launch": round(v[0] / max(v[1], 1) * 1e3, 2), "launches_per_forward": v[1] // 10,
+                          "ms_per_forward": round(v[0] / 10, 4)} for k, v in enc.profile_read(reset=True).items() if v[1]}
+            enc.profile(False)
         fl = cfg.flops_per_chunk() * B
         out[B] = {"eager_ms": statistics.median(ts), "graph_ms": statistics.median(tg),
                   "graph_tflops": fl / statistics.median(tg) / 1e9,
                   "utterances_per_s_graph": B / statistics.median(tg) * 1e3}
+        if stages:
+            out[B]["stages_eager"] = stages
         print(B, out[B], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "latency_small_batch.json"), "w"), indent=1)
