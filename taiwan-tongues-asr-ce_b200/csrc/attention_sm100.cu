@@ -164,6 +164,9 @@ __device__ __forceinline__ void exp2_poly_pair(uint32_t& a, uint32_t& b) {
 #ifndef TTASR_ATTN_LATEMAX
 #define TTASR_ATTN_LATEMAX 0
 #endif
+#ifndef TTASR_ATTN_SMSP_TOKEN
+#define TTASR_ATTN_SMSP_TOKEN 0
+#endif
 
 // POLY8: of every 8 consecutive scores of the chunk, the first POLY8 (even) take the polynomial, the rest MUFU.EX2
 template <int POLY8>
@@ -467,13 +470,24 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
     const uint32_t p_addr = tmem_base + lane_base + kColP + t * 64;
     const uint32_t o_addr = tmem_base + lane_base + kColO + t * kHeadDim;
     const bool leader = (wq == 0 && lane == 0);
-    constexpr uint32_t kTokBar = 2;         // +t: warpgroup t may start its exp sweep (the other one has finished its own)
+    // Token: warpgroup t may start its exp sweep (the other one has issued its last exponential).  The exp pipe is per
+    // scheduler, and warp wq of either warpgroup sits on scheduler wq — so with TTASR_ATTN_SMSP_TOKEN the token is
+    // passed between the two warps of each scheduler on their own (64-thread named barriers) instead of between whole
+    // warpgroups (256 threads: every hand-over then waits for the slowest of the four schedulers).
+#if TTASR_ATTN_SMSP_TOKEN
+    const uint32_t kTokBar = 2 + 2 * wq;    // +t; ids 2..9
+    constexpr uint32_t kTokThreads = 64;
+    constexpr uint32_t kEpiBar = 10;        // +t: warpgroup-local barrier of the output staging
+#else
+    constexpr uint32_t kTokBar = 2;         // +t
+    constexpr uint32_t kTokThreads = 256;
     constexpr uint32_t kEpiBar = 4;         // +t: warpgroup-local barrier of the output staging
+#endif
     uint32_t sphase = 0, ophase = 0;
     Tracer tr(1 + t, wq == 0 && lane == 0);
     const int last_valid = p.n_ctx - (p.kv_tiles - 1) * kTile;  // valid keys in the last KV tile
     const bool last_masked = last_valid < kTile;
-    if (t == 1) asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + 0), "r"(256) : "memory");  // warpgroup 0 sweeps first
+    if (t == 1) asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + 0), "r"(kTokThreads) : "memory");  // warpgroup 0 sweeps first
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       int b, h, q0;
       item_coords(item, b, h, q0);
@@ -575,7 +589,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           lsum += sum_pack(v, pk);
           tmem_st_32x16(p_addr + 16 * c, pk);
         };
-        auto tok_acquire = [&]() { tr(15); asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(256) : "memory"); tr(16); };
+        auto tok_acquire = [&]() { tr(15); asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(kTokThreads) : "memory"); tr(16); };
         if (kPreTokenChunks == 0) tok_acquire();
 #if TTASR_ATTN_LATEMAX
         {
@@ -596,7 +610,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         if (kPreTokenChunks == 3) tok_acquire();
         stage_a(v3, 3);
         if (kPreTokenChunks == 4) tok_acquire();
-        asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(256) : "memory");  // last exp issued
+        asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(kTokThreads) : "memory");  // last exp issued
         stage_b(v2, 2);
         stage_b(v3, 3);
         l += lsum;
@@ -643,7 +657,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
       tr(22);
     }
-    if (t == 0) asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + 0), "r"(256) : "memory");  // absorb the last token
+    if (t == 0) asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + 0), "r"(kTokThreads) : "memory");  // absorb the last token
     if (leader) tma_store_wait<0>();
   } else {
     TTASR_REG_DEC();  // warps 2-3: setmaxnreg is warpgroup-wide

@@ -321,31 +321,33 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
           else if (t0 + kTileFrames <= n_frames) run(MelEmit<1>{});
           else run(MelEmit<2>{});
         } else {
-        int m = mel.m0[wrp];
-        float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
-        __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
-        const unsigned char* pw = reinterpret_cast<const unsigned char*>(&s.tr[pw_col(lane)]);
-        float acc_a = 0.f, acc_b = 0.f;
-        const int op_end = mel.op_off[wrp + 1];
-        for (int oi = mel.op_off[wrp]; oi < op_end; ++oi) {
-          const int4 op = mel.ops[oi];
-          const float p = *reinterpret_cast<const float*>(pw + op.x);
-          acc_a = fmaf(__int_as_float(op.y), p, acc_a);
-          acc_b = fmaf(__int_as_float(op.z), p, acc_b);
-          if (op.w) {  // filter complete
-            const float v = mel_to_y(acc_a);
-            if (live) {
-              if (raw) *out_ptr = v;
-              tmax = fmaxf(tmax, v);
-              tmin = fminf(tmin, v);
+          int m = mel.m0[wrp];
+          float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
+          __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
+          const unsigned char* pw = reinterpret_cast<const unsigned char*>(&s.tr[pw_col(lane)]);
+          float acc_a = 0.f, acc_b = 0.f;
+          const int op_end = mel.op_off[wrp + 1];
+          // (Software-pipelining this loop by one op — next descriptor and power value requested before the current FMAs —
+          // was measured: 0.603 -> 0.618 ms per 256 chunks; the co-resident CTA already fills those stalls.)
+          for (int oi = mel.op_off[wrp]; oi < op_end; ++oi) {
+            const int4 op = mel.ops[oi];
+            const float p = *reinterpret_cast<const float*>(pw + op.x);
+            acc_a = fmaf(__int_as_float(op.y), p, acc_a);
+            acc_b = fmaf(__int_as_float(op.z), p, acc_b);
+            if (op.w) {  // filter complete
+              const float v = mel_to_y(acc_a);
+              if (live) {
+                if (raw) *out_ptr = v;
+                tmax = fmaxf(tmax, v);
+                tmin = fminf(tmin, v);
+              }
+              if (tmajor) *stg = __float2bfloat16_rn(v);
+              acc_a = acc_b;
+              acc_b = 0.f;
+              out_ptr += n_frames;
+              ++stg;
             }
-            if (tmajor) *stg = __float2bfloat16_rn(v);
-            acc_a = acc_b;
-            acc_b = 0.f;
-            out_ptr += n_frames;
-            ++stg;
           }
-        }
         }
       }
       __syncthreads();  // power spectra consumed before the next tile's pass 1 overwrites the buffer; staging complete

@@ -16,6 +16,11 @@ LM = "TTASR_ATTN_LATEMAX=1"
 VARIANTS = {
     "v2": [],                                   # two softmax warpgroups, 128-key tiles (attention_sm100.cu), as shipped
     "base": ["TTASR_ATTN_LATEMAX=0"],           # ... with the whole row max taken before the sweep (the round-1 chain)
+    "st": ["TTASR_ATTN_SMSP_TOKEN=1"],          # token passed per scheduler (64-thread barriers) instead of per warpgroup
+    "st_p2": ["TTASR_ATTN_SMSP_TOKEN=1", "TTASR_ATTN_PRETOKEN=2"],
+    "st_p0": ["TTASR_ATTN_SMSP_TOKEN=1", "TTASR_ATTN_PRETOKEN=0"],
+    "st_q2": ["TTASR_ATTN_SMSP_TOKEN=1", "TTASR_ATTN_POLY_Q0=2"],
+    "st_lm": ["TTASR_ATTN_SMSP_TOKEN=1", LM],
     "lm": [LM],                                 # quarter-0 max first, the rest beside quarter 0's exponentials
     "lm_n": [LM, "TTASR_ATTN_SETMAXNREG=1"],    # ... softmax warps at 224 registers
     "lm_p2": [LM, "TTASR_ATTN_PRETOKEN=2"],     # ... two quarters outside the token
