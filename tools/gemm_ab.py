@@ -11,7 +11,7 @@ def main():
     libs = [a.split("=", 1) for a in sys.argv[1:] if "=" in a and not a.startswith("--")]
     B = next((int(a) for a in sys.argv[1:] if a.isdigit()), 32)
     shape = next((a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--shape=")), "fc1")
-    N, K, act, f32 = {"fc1": (5120, 1280, 1, 0), "fc2": (1280, 5120, 0, 1), "qkv": (3840, 1280, 0, 0),
+    N, K, act, f32 = {"fc1": (5120, 1280, 1, 0), "fc2": (1280, 5120, 0, 1), "qkv": (3840, 1280, 0, 0), "fc1_noact": (5120, 1280, 0, 0),
                       "out_proj": (1280, 1280, 0, 1)}[shape]
     M = 1500 * B
     dev = torch.device("cuda", 0)
