@@ -145,6 +145,12 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
   __syncthreads();
 
   const bool rows_aligned = ((reinterpret_cast<uintptr_t>(pcm) & 15) == 0) && ((row_stride * sizeof(T)) % 16 == 0);
+  float2 w20;   // W20^sub = exp(-i pi sub / 10), the thread's constant of the twiddle symmetry in pass 1
+  {
+    double sn, cs;   // once per thread, in double so that the constant is correctly rounded like the table entries
+    sincospi(-0.1 * static_cast<double>(sub), &sn, &cs);
+    w20 = make_float2(static_cast<float>(cs), static_cast<float>(sn));
+  }
 
   // tile classification: 0 = all-zero (skip the transform), 1 = interior (bulk copy), 2 = edge (reflect / zero fill)
   auto classify = [&](int b, int tt, int& valid) -> int {
@@ -231,17 +237,31 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         float* ti = &s.ti[grp * kTStride + sub];
         tr[0] = yr[0];
         ti[0] = yi[0];
+        // twiddles W400^(n2 k1): k1 = 1..10 come from the table; W400^(n2 (20 - k1)) = W20^n2 * conj(W400^(n2 k1)) is
+        // derived with the thread's constant W20^n2 (4 FMA-pipe ops instead of 2 shared-memory loads: the load/store
+        // pipe is the busy one in this kernel)
 #pragma unroll
-        for (int k1 = 1; k1 < 20; ++k1) {
-          const float2 w = make_float2(s.tw_re[k1 * 20 + sub], s.tw_im[k1 * 20 + sub]);
-          tr[k1 * kTRow] = yr[k1] * w.x - yi[k1] * w.y;
-          ti[k1 * kTRow] = yr[k1] * w.y + yi[k1] * w.x;
+        for (int k1 = 1; k1 <= 10; ++k1) {
+          const float wx = s.tw_re[k1 * 20 + sub], wy = s.tw_im[k1 * 20 + sub];
+          tr[k1 * kTRow] = yr[k1] * wx - yi[k1] * wy;
+          ti[k1 * kTRow] = yr[k1] * wy + yi[k1] * wx;
+          if (k1 < 10) {
+            const int k1m = 20 - k1;
+            const float vx = fmaf(w20.x, wx, w20.y * wy), vy = fmaf(w20.y, wx, -(w20.x * wy));
+            tr[k1m * kTRow] = yr[k1m] * vx - yi[k1m] * vy;
+            ti[k1m * kTRow] = yr[k1m] * vy + yi[k1m] * vx;
+          }
         }
       }
       __syncthreads();
       // the PCM span is consumed: fetch the next tile's span under passes 2..4
       if (next < total_tiles) kind_next = stage(b_next, tt_next);
-      // ---------------- pass 2: thread (grp, k1) transforms over n2 -> Z[k1 + 20 k2]
+      // ---------------- pass 2: thread (grp, k1) transforms over n2 -> Z[k1 + 20 k2], then the Hermitian split + power of
+      // the two real frames (frame a = 2 grp in Re, frame b = 2 grp + 1 in Im).  A thread's own bins k = k1 + 20 i
+      // (i = 0..10, k <= 200) are exactly its outputs k2 = i and never leave the registers; only the partners Z[400 - k]
+      // — the upper half of the spectrum, k2 >= 10 — go through shared memory (half the stores and loads of a full
+      // round trip).  The spectra are then written bin-major, pw[k][frame] with a row pitch of 33 floats, so that in the
+      // mel pass lanes = frames read consecutive words (no bank conflicts) and the per-filter weight is a broadcast.
       {
         float yr[20], yi[20];
         const float* tr = &s.tr[grp * kTStride + sub * kTRow];
@@ -254,20 +274,17 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
 #pragma unroll
           for (int k2 = 0; k2 < 20; ++k2) c_unpack(y[k2], yr[k2], yi[k2]);
         }
-        __syncthreads();  // everyone has read its transpose rows; the buffer now becomes Z
-        float* zr = &s.tr[grp * kTStride + sub];
-        float* zi = &s.ti[grp * kTStride + sub];
+        __syncthreads();  // everyone has read its transpose rows; the buffer now takes the upper half of Z
+        {
+          float* zr = &s.tr[grp * kTStride + sub];
+          float* zi = &s.ti[grp * kTStride + sub];
 #pragma unroll
-        for (int k2 = 0; k2 < 20; ++k2) {
-          zr[20 * k2] = yr[k2];
-          zi[20 * k2] = yi[k2];
+          for (int k2 = 10; k2 < 20; ++k2) {
+            zr[20 * k2] = yr[k2];
+            zi[20 * k2] = yi[k2];
+          }
         }
-      }
-      __syncthreads();
-      // ---------------- Hermitian split + power: frame a = 2 grp, frame b = 2 grp + 1.  The spectra are written
-      // bin-major, pw[k][frame] with a row pitch of 33 floats, so that in the mel pass lanes = frames read
-      // consecutive words (no bank conflicts) and the per-filter weight is a broadcast.
-      {
+        __syncthreads();
         const float* zr = &s.tr[grp * kTStride];
         const float* zi = &s.ti[grp * kTStride];
         float pa[11], pb[11];
@@ -277,8 +294,10 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
           pa[i] = 0.f;
           pb[i] = 0.f;
           if (k < kNfreq) {
-            const int kk = (k == 0) ? 0 : kNfft - k;
-            split_power(zr[k], zi[k], zr[kk], zi[kk], pa[i], pb[i]);
+            // partner Z[(400 - k) mod 400]; bin 0 is its own partner (and lies in the half that is not stored)
+            const float wr = (k == 0) ? yr[0] : zr[kNfft - k];
+            const float wi = (k == 0) ? yi[0] : zi[kNfft - k];
+            split_power(yr[i], yi[i], wr, wi, pa[i], pb[i]);
           }
         }
         __syncthreads();  // all Z reads done; the (re) buffer now holds the power spectra
