@@ -161,7 +161,10 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
     if (rows_aligned && start >= 0 && start + kSpan <= valid) return 1;
     return 2;
   };
-  // bring a tile's PCM span into the staging buffer (asynchronously when interior); caller guarantees it is free
+  // bring a tile's PCM span into the staging buffer (asynchronously when interior); caller guarantees it is free.
+  // (Measured and dropped: staging the span in 320-sample blocks at a pitch of 340 words, which makes the pass-1 sample
+  // loads of the frame pairs sharing a warp conflict-free — 7 % fewer shared-memory wavefronts for 17 bulk copies per
+  // tile instead of one: 0.556 -> 0.554 ms per 256 chunks with the copies issued by 17 lanes, 0.570 by one.)
   auto stage = [&](int b, int tt) -> int {
     int valid;
     const int kind = classify(b, tt, valid);
