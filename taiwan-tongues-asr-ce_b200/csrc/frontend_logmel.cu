@@ -347,6 +347,10 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
           float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
           __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
           const unsigned char* pw = reinterpret_cast<const unsigned char*>(&s.tr[pw_col(lane)]);
+          // the per-filter completion path is kept free of per-lane branches and pointer tests: one store predicate, the
+          // staging row written unconditionally (it is shared memory), min / max folded in after the loop
+          const bool st_raw = live && raw != nullptr;
+          float vmax = -INFINITY, vmin = INFINITY;
           float acc_a = 0.f, acc_b = 0.f;
           const int op_end = mel.op_off[wrp + 1];
           // (Software-pipelining this loop by one op — next descriptor and power value requested before the current FMAs —
@@ -358,17 +362,19 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
             acc_b = fmaf(__int_as_float(op.z), p, acc_b);
             if (op.w) {  // filter complete
               const float v = mel_to_y(acc_a);
-              if (live) {
-                if (raw) *out_ptr = v;
-                tmax = fmaxf(tmax, v);
-                tmin = fminf(tmin, v);
-              }
-              if (tmajor) *stg = __float2bfloat16_rn(v);
+              if (st_raw) *out_ptr = v;
+              vmax = fmaxf(vmax, v);
+              vmin = fminf(vmin, v);
+              *stg = __float2bfloat16_rn(v);
               acc_a = acc_b;
               acc_b = 0.f;
               out_ptr += n_frames;
               ++stg;
             }
+          }
+          if (live) {
+            tmax = fmaxf(tmax, vmax);
+            tmin = fminf(tmin, vmin);
           }
         }
       }
