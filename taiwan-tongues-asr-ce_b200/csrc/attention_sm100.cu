@@ -167,6 +167,9 @@ __device__ __forceinline__ void exp2_poly_pair(uint32_t& a, uint32_t& b) {
 #ifndef TTASR_ATTN_SMSP_TOKEN
 #define TTASR_ATTN_SMSP_TOKEN 0
 #endif
+#ifndef TTASR_ATTN_EARLY_RELEASE
+#define TTASR_ATTN_EARLY_RELEASE 0
+#endif
 
 // POLY8: of every 8 consecutive scores of the chunk, the first POLY8 (even) take the polynomial, the rest MUFU.EX2
 template <int POLY8>
@@ -608,9 +611,15 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         stage_a(v2, 2);
         stage_b(v1, 1);
         if (kPreTokenChunks == 3) tok_acquire();
+#if TTASR_ATTN_EARLY_RELEASE
+        // hand the token over one quarter early: the other warpgroup's wake-up then overlaps the tail of this sweep
+        asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(kTokThreads) : "memory");
+        stage_a(v3, 3);
+#else
         stage_a(v3, 3);
         if (kPreTokenChunks == 4) tok_acquire();
         asm volatile("bar.arrive %0, %1;" ::"r"(kTokBar + (1 - t)), "r"(kTokThreads) : "memory");  // last exp issued
+#endif
         stage_b(v2, 2);
         stage_b(v3, 3);
         l += lsum;

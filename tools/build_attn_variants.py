@@ -16,6 +16,10 @@ LM = "TTASR_ATTN_LATEMAX=1"
 VARIANTS = {
     "v2": [],                                   # two softmax warpgroups, 128-key tiles (attention_sm100.cu), as shipped
     "base": ["TTASR_ATTN_LATEMAX=0"],           # ... with the whole row max taken before the sweep (the round-1 chain)
+    "er": ["TTASR_ATTN_EARLY_RELEASE=1"],       # token handed over before the last quarter's exponentials
+    "er_p0": ["TTASR_ATTN_EARLY_RELEASE=1", "TTASR_ATTN_PRETOKEN=0"],
+    "er_st": ["TTASR_ATTN_EARLY_RELEASE=1", "TTASR_ATTN_SMSP_TOKEN=1"],
+    "er_st_p0": ["TTASR_ATTN_EARLY_RELEASE=1", "TTASR_ATTN_SMSP_TOKEN=1", "TTASR_ATTN_PRETOKEN=0"],
     "st": ["TTASR_ATTN_SMSP_TOKEN=1"],          # token passed per scheduler (64-thread barriers) instead of per warpgroup
     "st_p2": ["TTASR_ATTN_SMSP_TOKEN=1", "TTASR_ATTN_PRETOKEN=2"],
     "st_p0": ["TTASR_ATTN_SMSP_TOKEN=1", "TTASR_ATTN_PRETOKEN=0"],
