@@ -170,6 +170,12 @@ __device__ __forceinline__ void exp2_poly_pair(uint32_t& a, uint32_t& b) {
 #ifndef TTASR_ATTN_EARLY_RELEASE
 #define TTASR_ATTN_EARLY_RELEASE 0
 #endif
+#ifndef TTASR_ATTN_FAKE_EXP
+#define TTASR_ATTN_FAKE_EXP 0
+#endif
+#ifndef TTASR_ATTN_TWO_MMA
+#define TTASR_ATTN_TWO_MMA 0
+#endif
 
 // POLY8: of every 8 consecutive scores of the chunk, the first POLY8 (even) take the polynomial, the rest MUFU.EX2
 template <int POLY8>
@@ -189,6 +195,11 @@ __device__ __forceinline__ void exp_inplace(uint32_t (&v)[32], float m_used) {
         : "r"(__float_as_uint(kLog2e)), "r"(__float_as_uint(neg_m)));
     if ((i & 7) < POLY8) {
       exp2_poly_pair(v[i], v[i + 1]);
+#if TTASR_ATTN_FAKE_EXP   // diagnostic builds only (wrong results): that many of every 8 exponentials cost nothing
+    } else if ((i & 7) < TTASR_ATTN_FAKE_EXP) {
+      v[i] &= 0x3fffffffu;
+      v[i + 1] &= 0x3fffffffu;
+#endif
     } else {
       v[i] = __float_as_uint(ex2(__uint_as_float(v[i])));
       v[i + 1] = __float_as_uint(ex2(__uint_as_float(v[i + 1])));
@@ -273,10 +284,10 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
   }
   if (warp == 1 && lane == 0) {
     mbar_init(smem_u32(&s.q_full), 1);
-    mbar_init(smem_u32(&s.q_free), 1);
+    mbar_init(smem_u32(&s.q_free), TTASR_ATTN_TWO_MMA ? 2 : 1);
     for (int i = 0; i < kKvStages; ++i) {
       mbar_init(smem_u32(&s.kv_full[i]), 1);
-      mbar_init(smem_u32(&s.kv_free[i]), 1);
+      mbar_init(smem_u32(&s.kv_free[i]), TTASR_ATTN_TWO_MMA ? 2 : 1);
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(smem_u32(&s.s_full[t]), 1);
@@ -348,6 +359,80 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
       }
     }
+#if TTASR_ATTN_TWO_MMA
+  } else if (warp == 1 || warp == 3) {
+    // ===================================================== one MMA issuer PER QUERY TILE (experiment): warp 1 serves
+    // tile 0, warp 3 tile 1, each in its own order (S_t(j+1) when S_t(j) has been read out, PV_t(j) when P_t(j) is
+    // ready), so neither warpgroup's hand-overs queue behind the other's in a shared program order.  K/V stages and Q are
+    // released when both issuers have committed (barrier count 2).
+    TTASR_REG_DEC();
+    {
+      const int t = (warp == 1) ? 0 : 1;
+      constexpr uint32_t idesc_s = umma_idesc_bf16(kTile, kTile, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(kTile, kHeadDim, 0, 1);
+      int stage = 0;            // stage of KV tile j+1 (S look-ahead)
+      uint32_t phase = 0, qphase = 0, pphase = 0, fphase = 0;
+      auto issue_s = [&](int st) {
+        const uint64_t adesc = umma_desc_sw128(smem_u32(&s.q[t][0]), 16, 1024);
+        const uint64_t bdesc = umma_desc_sw128(smem_u32(&s.k[st][0]), 16, 1024);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kHeadDim / 16; ++k)
+            umma_ss<1>(tmem_base + kColS + t * kTile, adesc + 2 * k, bdesc + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(smem_u32(&s.s_full[t]));
+        }
+        __syncwarp();
+      };
+      auto commit = [&](unsigned long long* bar) {
+        if (elect_one()) umma_commit(smem_u32(bar));
+        __syncwarp();
+      };
+      auto issue_pv = [&](int st, bool first) {
+        const uint64_t vdesc = umma_desc_sw128(smem_u32(&s.v[st][0]), kTileBytes, 1024);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kTile / 16; ++k)
+            umma_ts(tmem_base + kColO + t * kHeadDim, tmem_base + kColP + t * 64 + k * 8, vdesc + 128 * k, idesc_o,
+                    (first && k == 0) ? 0u : 1u);
+          umma_commit(smem_u32(&s.o_done[t]));
+        }
+        __syncwarp();
+      };
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        mbar_wait(smem_u32(&s.q_full), qphase);
+        qphase ^= 1;
+        mbar_wait(smem_u32(&s.kv_full[stage]), phase);
+        tc_fence_after();
+        issue_s(stage);
+        if (p.kv_tiles == 1) commit(&s.q_free);
+        int cur = stage;
+        if (++stage == kKvStages) { stage = 0; phase ^= 1; }
+        for (int j = 0; j < p.kv_tiles; ++j) {
+          const bool more = (j + 1 < p.kv_tiles);
+          if (more) {
+            mbar_wait(smem_u32(&s.kv_full[stage]), phase);
+            tc_fence_after();
+          }
+          mbar_wait(smem_u32(&s.s_free[t]), fphase);
+          fphase ^= 1;
+          tc_fence_after();
+          if (more) {
+            issue_s(stage);
+            if (j + 2 == p.kv_tiles) commit(&s.q_free);  // last S of the item issued
+          }
+          mbar_wait(smem_u32(&s.p_ready[t]), pphase);
+          pphase ^= 1;
+          tc_fence_after();
+          issue_pv(cur, j == 0);
+          commit(&s.kv_free[cur]);  // this tile's MMAs on KV tile j are issued (the other issuer commits its own)
+          if (more) {
+            cur = stage;
+            if (++stage == kKvStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+#else
   } else if (warp == 1) {
     // ===================================================== MMA issuer (uniform control flow, one elected lane
     // issues: each tcgen05.mma is then a single UTCHMMA on precomputed uniform registers instead of a per-instruction
@@ -462,6 +547,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         commit(&s.kv_free[prev]);
       }
     }
+#endif  // TTASR_ATTN_TWO_MMA
   } else if (warp >= 4) {
     // ===================================================== softmax + output, one thread per query row
     TTASR_REG_INC();

@@ -16,6 +16,13 @@ LM = "TTASR_ATTN_LATEMAX=1"
 VARIANTS = {
     "v2": [],                                   # two softmax warpgroups, 128-key tiles (attention_sm100.cu), as shipped
     "base": ["TTASR_ATTN_LATEMAX=0"],           # ... with the whole row max taken before the sweep (the round-1 chain)
+    "mma2": ["TTASR_ATTN_TWO_MMA=1"],           # one MMA-issuing warp per query tile
+    "mma2_p0": ["TTASR_ATTN_TWO_MMA=1", "TTASR_ATTN_PRETOKEN=0"],
+    "mma2_st": ["TTASR_ATTN_TWO_MMA=1", "TTASR_ATTN_SMSP_TOKEN=1"],
+    "mma2_fake8": ["TTASR_ATTN_TWO_MMA=1", "TTASR_ATTN_FAKE_EXP=8"],
+    "fake2": ["TTASR_ATTN_FAKE_EXP=2"],         # diagnostic (wrong results): 2 / 4 / 8 of every 8 exponentials are free
+    "fake4": ["TTASR_ATTN_FAKE_EXP=4"],
+    "fake8": ["TTASR_ATTN_FAKE_EXP=8"],
     "er": ["TTASR_ATTN_EARLY_RELEASE=1"],       # token handed over before the last quarter's exponentials
     "er_p0": ["TTASR_ATTN_EARLY_RELEASE=1", "TTASR_ATTN_PRETOKEN=0"],
     "er_st": ["TTASR_ATTN_EARLY_RELEASE=1", "TTASR_ATTN_SMSP_TOKEN=1"],
