@@ -176,6 +176,15 @@ __device__ __forceinline__ void exp2_poly_pair(uint32_t& a, uint32_t& b) {
 #ifndef TTASR_ATTN_TWO_MMA
 #define TTASR_ATTN_TWO_MMA 0
 #endif
+// TTASR_ATTN_POLL=1 (experiment): the kernel's mbarrier waits poll with test_wait instead of the suspending try_wait
+#ifndef TTASR_ATTN_POLL
+#define TTASR_ATTN_POLL 0
+#endif
+#if TTASR_ATTN_POLL
+#define ATTN_WAIT mbar_wait_poll
+#else
+#define ATTN_WAIT mbar_wait
+#endif
 
 // POLY8: of every 8 consecutive scores of the chunk, the first POLY8 (even) take the polynomial, the rest MUFU.EX2
 template <int POLY8>
@@ -336,7 +345,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         int b, h, q0;
         item_coords(item, b, h, q0);
-        mbar_wait(smem_u32(&s.q_free), qphase ^ 1);
+        ATTN_WAIT(smem_u32(&s.q_free), qphase ^ 1);
         qphase ^= 1;
         if (elect_one()) {
           mbar_arrive_expect_tx(smem_u32(&s.q_full), 2 * kTileBytes);
@@ -346,7 +355,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         __syncwarp();
         for (int j = 0; j < p.kv_tiles; ++j) {
           tr(50);
-          mbar_wait(smem_u32(&s.kv_free[stage]), phase ^ 1);
+          ATTN_WAIT(smem_u32(&s.kv_free[stage]), phase ^ 1);
           tr(51);
           if (elect_one()) {
             const uint32_t bar = smem_u32(&s.kv_full[stage]);
@@ -399,9 +408,9 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         __syncwarp();
       };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        mbar_wait(smem_u32(&s.q_full), qphase);
+        ATTN_WAIT(smem_u32(&s.q_full), qphase);
         qphase ^= 1;
-        mbar_wait(smem_u32(&s.kv_full[stage]), phase);
+        ATTN_WAIT(smem_u32(&s.kv_full[stage]), phase);
         tc_fence_after();
         issue_s(stage);
         if (p.kv_tiles == 1) commit(&s.q_free);
@@ -410,17 +419,17 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         for (int j = 0; j < p.kv_tiles; ++j) {
           const bool more = (j + 1 < p.kv_tiles);
           if (more) {
-            mbar_wait(smem_u32(&s.kv_full[stage]), phase);
+            ATTN_WAIT(smem_u32(&s.kv_full[stage]), phase);
             tc_fence_after();
           }
-          mbar_wait(smem_u32(&s.s_free[t]), fphase);
+          ATTN_WAIT(smem_u32(&s.s_free[t]), fphase);
           fphase ^= 1;
           tc_fence_after();
           if (more) {
             issue_s(stage);
             if (j + 2 == p.kv_tiles) commit(&s.q_free);  // last S of the item issued
           }
-          mbar_wait(smem_u32(&s.p_ready[t]), pphase);
+          ATTN_WAIT(smem_u32(&s.p_ready[t]), pphase);
           pphase ^= 1;
           tc_fence_after();
           issue_pv(cur, j == 0);
@@ -484,22 +493,22 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       };
       auto wait_p = [&](int t) {
         tr(30 + t);
-        mbar_wait(smem_u32(&s.p_ready[t]), pphase[t]);
+        ATTN_WAIT(smem_u32(&s.p_ready[t]), pphase[t]);
         pphase[t] ^= 1;
         tc_fence_after();
         tr(32 + t);
       };
       auto wait_sfree = [&](int t) {
         tr(40 + t);
-        mbar_wait(smem_u32(&s.s_free[t]), fphase[t]);
+        ATTN_WAIT(smem_u32(&s.s_free[t]), fphase[t]);
         fphase[t] ^= 1;
         tc_fence_after();
         tr(42 + t);
       };
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        mbar_wait(smem_u32(&s.q_full), qphase);
+        ATTN_WAIT(smem_u32(&s.q_full), qphase);
         qphase ^= 1;
-        mbar_wait(smem_u32(&s.kv_full[stage]), phase);
+        ATTN_WAIT(smem_u32(&s.kv_full[stage]), phase);
         tc_fence_after();
         issue_s(0, stage);
         issue_s(1, stage);
@@ -514,7 +523,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           const bool more = (j + 1 < p.kv_tiles);
           if (more) {
             tr(44);
-            mbar_wait(smem_u32(&s.kv_full[stage]), phase);
+            ATTN_WAIT(smem_u32(&s.kv_full[stage]), phase);
             tc_fence_after();
             tr(45);
             wait_sfree(0);
@@ -585,7 +594,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       for (int j = 0; j < p.kv_tiles; ++j) {
         const bool masked = last_masked && (j == p.kv_tiles - 1);
         tr(10);
-        mbar_wait(smem_u32(&s.s_full[t]), sphase);
+        ATTN_WAIT(smem_u32(&s.s_full[t]), sphase);
         sphase ^= 1;
         tc_fence_after();
         tr(11);
@@ -609,7 +618,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         bool o_waited = (j == 0);
         auto wait_o = [&]() {
           if (!o_waited) {
-            mbar_wait(smem_u32(&s.o_done[t]), ophase);
+            ATTN_WAIT(smem_u32(&s.o_done[t]), ophase);
             ophase ^= 1;
             tc_fence_after();
             o_waited = true;
@@ -718,7 +727,7 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
       }
       // ---- epilogue: O / l -> bf16 -> swizzled smem -> TMA store
       tr(20);
-      mbar_wait(smem_u32(&s.o_done[t]), ophase);
+      ATTN_WAIT(smem_u32(&s.o_done[t]), ophase);
       tr(21);
       ophase ^= 1;
       tc_fence_after();

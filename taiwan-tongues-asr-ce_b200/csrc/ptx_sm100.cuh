@@ -114,6 +114,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if ((++spins & 1023u) == 0) mbar_timeout_check(t0);
   }
 }
+// the same without the hardware suspend: mbarrier.test_wait returns at once, the loop polls.  For waits on the latency
+// path of a hand-over chain (attention), where the wake-up of a suspended try_wait would add to every hop.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint32_t bar, uint32_t parity) {
+  if (mbar_test_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 0xffffu) == 0) mbar_timeout_check(t0);
+  }
+}
 // acquire at cluster scope: needed when the arrive came from the peer CTA's generic-proxy thread
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();

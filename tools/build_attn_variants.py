@@ -16,6 +16,9 @@ LM = "TTASR_ATTN_LATEMAX=1"
 VARIANTS = {
     "v2": [],                                   # two softmax warpgroups, 128-key tiles (attention_sm100.cu), as shipped
     "base": ["TTASR_ATTN_LATEMAX=0"],           # ... with the whole row max taken before the sweep (the round-1 chain)
+    "poll": ["TTASR_ATTN_POLL=1"],              # mbarrier waits poll (test_wait) instead of suspending (try_wait)
+    "poll_mma2": ["TTASR_ATTN_POLL=1", "TTASR_ATTN_TWO_MMA=1"],
+    "poll_fake8": ["TTASR_ATTN_POLL=1", "TTASR_ATTN_FAKE_EXP=8"],
     "mma2": ["TTASR_ATTN_TWO_MMA=1"],           # one MMA-issuing warp per query tile
     "mma2_p0": ["TTASR_ATTN_TWO_MMA=1", "TTASR_ATTN_PRETOKEN=0"],
     "mma2_st": ["TTASR_ATTN_TWO_MMA=1", "TTASR_ATTN_SMSP_TOKEN=1"],
