@@ -176,6 +176,11 @@ __device__ __forceinline__ void exp2_poly_pair(uint32_t& a, uint32_t& b) {
 #ifndef TTASR_ATTN_TWO_MMA
 #define TTASR_ATTN_TWO_MMA 0
 #endif
+// TTASR_ATTN_ABLATE (diagnostic builds only, wrong results): bit 0 = no row max, bit 1 = no P store to TMEM,
+// bit 2 = only the first quarter of S is loaded from TMEM, bit 3 = no bf16 packing / row sums
+#ifndef TTASR_ATTN_ABLATE
+#define TTASR_ATTN_ABLATE 0
+#endif
 // TTASR_ATTN_POLL=1 (experiment): the kernel's mbarrier waits poll with test_wait instead of the suspending try_wait
 #ifndef TTASR_ATTN_POLL
 #define TTASR_ATTN_POLL 0
@@ -600,10 +605,16 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         tr(11);
         uint32_t v0[32], v1[32], v2[32], v3[32];
         tmem_ld_32x32(s_addr, v0);
+#if TTASR_ATTN_ABLATE & 4
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v1[i] = v0[i] ^ 1u; v2[i] = v0[i] ^ 2u; v3[i] = v0[i] ^ 3u; }
+#else
         tmem_ld_32x32(s_addr + 32, v1);
         tmem_ld_32x32(s_addr + 64, v2);
         tmem_ld_32x32(s_addr + 96, v3);
         tmem_wait_ld();
+#endif
         tr(12);
         tc_fence_before();
         __syncwarp();
@@ -658,7 +669,11 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
         }
         tr(14);
 #else
+#if TTASR_ATTN_ABLATE & 1
+        const float mx = __uint_as_float(v0[0]);
+#else
         const float mx = fmaxf(fmaxf(chunk_max(v0), chunk_max(v1)), fmaxf(chunk_max(v2), chunk_max(v3)));
+#endif
         const float m_tile = mx * kLog2e;
         tr(13);
         // (Deferring this wait into the sweep was measured slower: it then sits inside the token-exclusive section.)
@@ -684,8 +699,31 @@ __global__ void __launch_bounds__(kAttnThreads, 1) attention_kernel(const __grid
           else exp_inplace<TTASR_ATTN_POLY_Q3>(v, m_used);
         };
         auto stage_b = [&](const uint32_t (&v)[32], int c) {
+#if TTASR_ATTN_ABLATE & 8        // no bf16 conversion (one LOP3 per pair keeps every exponential live), sums kept
+          {
+            uint32_t s0 = 0u, s1 = 0u;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              asm("{ .reg .b64 t, u;\n\tmov.b64 t, {%0, %1};\n\tmov.b64 u, {%2, %3};\n\tadd.rn.f32x2 t, t, u;\n\tmov.b64 {%0, %1}, t; }"
+                  : "+r"(s0), "+r"(s1) : "r"(v[2 * i]), "r"(v[2 * i + 1]));
+              pk[i] = v[2 * i] ^ v[2 * i + 1];
+            }
+            lsum += __uint_as_float(s0) + __uint_as_float(s1);
+          }
+#elif TTASR_ATTN_ABLATE & 16     // no row sums, conversion kept
+          {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            lsum += __uint_as_float(pk[c]);
+          }
+#else
           lsum += sum_pack(v, pk);
+#endif
+#if !(TTASR_ATTN_ABLATE & 2)
           tmem_st_32x16(p_addr + 16 * c, pk);
+#else
+          if (c == 3) tmem_st_32x16(p_addr + 16 * c, pk);
+#endif
         };
         auto tok_acquire = [&]() { tr(15); asm volatile("bar.sync %0, %1;" ::"r"(kTokBar + t), "r"(kTokThreads) : "memory"); tr(16); };
         if (kPreTokenChunks == 0) tok_acquire();

@@ -16,6 +16,12 @@ LM = "TTASR_ATTN_LATEMAX=1"
 VARIANTS = {
     "v2": [],                                   # two softmax warpgroups, 128-key tiles (attention_sm100.cu), as shipped
     "base": ["TTASR_ATTN_LATEMAX=0"],           # ... with the whole row max taken before the sweep (the round-1 chain)
+    "abl_max": ["TTASR_ATTN_ABLATE=1"],         # diagnostics (wrong results): one element of the chain removed at a time
+    "abl_st": ["TTASR_ATTN_ABLATE=2"],
+    "abl_ld": ["TTASR_ATTN_ABLATE=4"],
+    "abl_pack": ["TTASR_ATTN_ABLATE=8"],
+    "abl_sum": ["TTASR_ATTN_ABLATE=16"],
+    "abl_all": ["TTASR_ATTN_ABLATE=15", "TTASR_ATTN_FAKE_EXP=8"],
     "poll": ["TTASR_ATTN_POLL=1"],              # mbarrier waits poll (test_wait) instead of suspending (try_wait)
     "poll_mma2": ["TTASR_ATTN_POLL=1", "TTASR_ATTN_TWO_MMA=1"],
     "poll_fake8": ["TTASR_ATTN_POLL=1", "TTASR_ATTN_FAKE_EXP=8"],
