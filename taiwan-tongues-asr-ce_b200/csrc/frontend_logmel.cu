@@ -324,12 +324,15 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         const int lane = tid & 31;
         const int wrp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler: constant-bank indexing
         const bool live = (t0 + lane) < n_frames;
+        // pitch of the bf16 staging rows (one per frame): the staging store is unconditional, so without a time-major
+        // output the rows still must not overlap (they are simply never copied out)
+        const int stg_ld = tmajor ? tmajor_ld : kMaxMels;
         if constexpr (MELB != 0) {
           // the bank is known at compile time: straight-line LDS + FFMA per bin, weights and offsets as immediates
           auto run = [&](auto o) {
             o.out = raw + static_cast<long long>(b) * MELB * n_frames + t0 + lane;
             o.nf = n_frames;
-            o.stg = reinterpret_cast<uint32_t*>(&s.ti[0]) + lane * ((tmajor_ld >> 1) + 1);   // ti is idle by now
+            o.stg = reinterpret_cast<uint32_t*>(&s.ti[0]) + lane * ((stg_ld >> 1) + 1);   // ti is idle by now
             o.vmax = -INFINITY;
             o.vmin = INFINITY;
             o.live = live;
@@ -345,7 +348,7 @@ logmel_frames_kernel(const T* __restrict__ pcm, long long row_stride, const int*
         } else {
           int m = mel.m0[wrp];
           float* out_ptr = raw + (static_cast<long long>(b) * n_mels + m) * n_frames + t0 + lane;
-          __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (tmajor_ld + 2) + m;  // ti is idle by now
+          __nv_bfloat16* stg = reinterpret_cast<__nv_bfloat16*>(&s.ti[0]) + lane * (stg_ld + 2) + m;  // ti is idle by now
           const unsigned char* pw = reinterpret_cast<const unsigned char*>(&s.tr[pw_col(lane)]);
           // the per-filter completion path is kept free of per-lane branches and pointer tests: one store predicate, the
           // staging row written unconditionally (it is shared memory), min / max folded in after the loop

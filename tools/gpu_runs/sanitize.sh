@@ -9,6 +9,6 @@ timeout 900 $CS --tool memcheck --error-exitcode 9 --print-limit 20 python -m py
 echo "rc=$?" >> gpurun_out/r2_sanitizer_memcheck_ops.log
 timeout 900 $CS --tool memcheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_frontend.py tests/test_gpu_encoder.py -q -x --timeout=800 -k "config1_clips or ragged or clamp_pass or (matches_fp32_oracle and micro) or (residual_modes and micro)" > gpurun_out/r2_sanitizer_memcheck_path.log 2>&1
 echo "rc=$?" >> gpurun_out/r2_sanitizer_memcheck_path.log
-timeout 600 $CS --tool racecheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_frontend.py -q -x --timeout=500 -k "config1_clips and 80 or padding_tiles" > gpurun_out/r2_sanitizer_racecheck_frontend.log 2>&1
+timeout 600 $CS --tool racecheck --error-exitcode 9 --print-limit 20 python -m pytest tests/test_gpu_frontend.py -q -x --timeout=500 -k "config1_clips or padding_tiles or compiled_in" > gpurun_out/r2_sanitizer_racecheck_frontend.log 2>&1
 echo "rc=$?" >> gpurun_out/r2_sanitizer_racecheck_frontend.log
 tail -4 gpurun_out/r2_sanitizer_*.log
